@@ -1,0 +1,53 @@
+"""Seeded synthetic datasets shaped like BASELINE.json's configs.
+
+I.i.d. uniform data is pathologically hard for graph search (distance concentration), so the graph
+configs use a low-rank latent model  x = z A + 0.05 eps,  z ~ N(0, I_L),  A ~ N(0, 1/L)^(L x d),
+which the survey calibrated to SIFT-like difficulty (L=16 at d=128).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["low_rank", "uniform", "integer_grid", "CONFIGS"]
+
+# name -> (n, dim, nq, latent L, metric, quant, topk)
+CONFIGS = {
+    "quickstart": (1000, 128, 10, 0, "l2", "none", 10),
+    "sift1m": (1_000_000, 128, 10_000, 16, "l2", "none", 10),
+    "gist960": (1_000_000, 960, 10_000, 48, "l2", "sq8", 10),
+    "rag768": (5_000_000, 768, 10_000, 48, "ip", "sq4", 100),
+    "deep100m": (100_000_000, 96, 10_000, 24, "l2", "none", 10),
+}
+
+
+def low_rank(n: int, dim: int, nq: int, latent: int = 16, seed: int = 42, noise: float = 0.05, normalize: bool = False, chunk: int = 1 << 18):
+    """Base [n, dim] and queries [nq, dim], float32, from one seeded stream (A, then base, then queries)."""
+    rng = np.random.default_rng(seed)
+    a = (rng.standard_normal((latent, dim)) / np.sqrt(latent)).astype(np.float32)
+
+    def gen(m):
+        out = np.empty((m, dim), np.float32)
+        for s in range(0, m, chunk):
+            e = min(m, s + chunk)
+            z = rng.standard_normal((e - s, latent), dtype=np.float32)
+            out[s:e] = z @ a
+            out[s:e] += noise * rng.standard_normal((e - s, dim), dtype=np.float32)
+        if normalize:
+            out /= np.linalg.norm(out, axis=1, keepdims=True)
+        return out
+
+    return gen(n), gen(nq)
+
+
+def uniform(n: int, dim: int, nq: int, seed: int = 0):
+    """README quickstart shape: np.random.rand-like data (python/tests/test_index_types.py:32-40)."""
+    rng = np.random.default_rng(seed)
+    return rng.random((n, dim), dtype=np.float32), rng.random((nq, dim), dtype=np.float32)
+
+
+def integer_grid(n: int, dim: int, nq: int, seed: int = 7, hi: int = 16):
+    """Small-integer coordinates stored as float32: every fp32 sum on the path is exact, so results
+    are independent of summation order and must match the reference bit for bit, ties included."""
+    rng = np.random.default_rng(seed)
+    return (rng.integers(0, hi, (n, dim)).astype(np.float32), rng.integers(0, hi, (nq, dim)).astype(np.float32))
