@@ -1,0 +1,262 @@
+"""ctypes view of the C ABI (include/alaya_b200.h) for tools that sit below the SDK: the parity
+tests, bench.py and the multi-GPU sharding helper. Host numpy arrays in, numpy arrays out; the
+*_device functions take raw device pointers (e.g. torch tensors' data_ptr())."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libalaya_b200.so")
+
+u8p, u32p, u64p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
+METRICS = {"l2": 0, "euclidean": 0, "ip": 1, "cos": 2, "cosine": 2}
+QUANTS = {"none": 0, None: 0, "sq8": 1, "sq4": 2}
+INDEX_TYPES = {"flat": 0, "hnsw": 1, "nsg": 2, "fusion": 3}
+
+# every symbol include/alaya_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "ab_index_create", "ab_index_destroy", "ab_index_fit", "ab_index_search", "ab_index_batch_search",
+    "ab_index_batch_search_with_distance", "ab_index_insert", "ab_index_remove", "ab_index_get_data_by_id",
+    "ab_index_get_dim", "ab_index_get_size", "ab_index_save", "ab_index_load", "ab_index_batch_search_device",
+    "ab_index_fit_spaces", "ab_index_set_graph", "ab_index_build_graph", "ab_index_graph_info", "ab_index_get_graph",
+    "ab_index_get_codes", "ab_index_search_stats", "ab_index_batch_traverse", "ab_distance_pairs", "ab_quant_fit_encode",
+    "ab_normalize_rows", "ab_bruteforce_topk", "ab_bruteforce_topk_device", "ab_merge_topk_device", "ab_last_error",
+    "ab_device_count", "ab_set_device", "ab_kernel_launch_count", "ab_version",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("index_type", C.c_int32), ("quantization_type", C.c_int32), ("metric", C.c_int32), ("capacity", C.c_uint32),
+                ("max_nbrs", C.c_uint32), ("device", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m alayalite_b200.build`; there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ab_last_error.restype = C.c_char_p
+        _lib.ab_version.restype = C.c_char_p
+        _lib.ab_kernel_launch_count.restype = C.c_uint64
+        _lib.ab_index_get_dim.restype = C.c_uint32
+        _lib.ab_index_get_size.restype = C.c_uint64
+        _lib.ab_index_get_dim.argtypes = [C.c_void_p]
+        _lib.ab_index_get_size.argtypes = [C.c_void_p]
+        _lib.ab_index_destroy.argtypes = [C.c_void_p]
+    return _lib
+
+
+class AbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        raise AbError(rc, lib().ab_last_error().decode())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _vp(x):
+    return C.c_void_p(int(x)) if x is not None else C.c_void_p(0)
+
+
+def kernel_launch_count() -> int:
+    return int(lib().ab_kernel_launch_count())
+
+
+def device_count() -> int:
+    return int(lib().ab_device_count())
+
+
+class NativeIndex:
+    """Thin owner of one ab_index handle."""
+
+    def __init__(self, metric="l2", quant="none", capacity=100000, index_type="hnsw", device=-1, handle=None):
+        self.metric, self.quant, self.capacity = metric, quant, capacity
+        self._own = handle is None
+        if handle is None:
+            p = Params(INDEX_TYPES[index_type], QUANTS[quant], METRICS[metric], capacity, 32, device)
+            h = C.c_void_p()
+            check(lib().ab_index_create(C.byref(p), C.byref(h)))
+            self.h = h
+        else:
+            self.h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "_own", False) and getattr(self, "h", None):
+            lib().ab_index_destroy(self.h)
+            self.h = None
+
+    @property
+    def dim(self):
+        return int(lib().ab_index_get_dim(self.h))
+
+    @property
+    def size(self):
+        return int(lib().ab_index_get_size(self.h))
+
+    def row_bytes(self):
+        return self.dim if self.quant == "sq8" else (self.dim + 1) // 2
+
+    def fit(self, data, ef_construction=100, num_threads=1):
+        d = _f32(data)
+        check(lib().ab_index_fit(self.h, _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]), C.c_uint32(ef_construction), C.c_uint32(num_threads)))
+
+    def fit_spaces(self, data):
+        d = _f32(data)
+        check(lib().ab_index_fit_spaces(self.h, _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1])))
+
+    def build_graph(self, ef_construction=100):
+        check(lib().ab_index_build_graph(self.h, C.c_uint32(ef_construction)))
+
+    def set_graph(self, adj, levels, lists_flat, ep):
+        adj = np.ascontiguousarray(adj, np.uint32)
+        lists_flat = np.ascontiguousarray(lists_flat, np.uint32)
+        lv = None if levels is None else np.ascontiguousarray(levels, np.uint32)
+        check(lib().ab_index_set_graph(self.h, _p(adj, u32p), _p(lv, u32p) if lv is not None else None,
+                                       _p(lists_flat, u32p) if lists_flat.size else None, C.c_uint64(lists_flat.size), C.c_uint32(ep)))
+
+    def graph(self):
+        info = (C.c_uint64 * 5)()
+        check(lib().ab_index_graph_info(self.h, info))
+        n, R, ep, ll = int(info[0]), int(info[1]), int(info[2]), int(info[3])
+        adj = np.zeros((n, R), np.uint32)
+        levels = np.zeros(n, np.uint32)
+        lists = np.zeros(max(ll, 1), np.uint32)
+        check(lib().ab_index_get_graph(self.h, _p(adj, u32p), _p(levels, u32p), _p(lists, u32p)))
+        return dict(adj=adj, levels=levels, lists_flat=lists[:ll], ep=ep, R=R, capacity=int(info[4]))
+
+    def codes(self):
+        n, d = self.size, self.dim
+        codes = np.zeros((n, self.row_bytes()), np.uint8)
+        mn, mx = np.zeros(d, np.float32), np.zeros(d, np.float32)
+        check(lib().ab_index_get_codes(self.h, _p(codes, u8p), _p(mn, f32p), _p(mx, f32p)))
+        return mn, mx, codes
+
+    def get_data_by_id(self, i):
+        out = np.zeros(self.dim, np.float32)
+        check(lib().ab_index_get_data_by_id(self.h, C.c_uint32(i), _p(out, f32p)))
+        return out
+
+    def search(self, query, topk, ef=100):
+        q = _f32(query)
+        ids = np.zeros(topk, np.uint32)
+        check(lib().ab_index_search(self.h, _p(q, f32p), C.c_uint32(topk), C.c_uint32(ef), _p(ids, u32p)))
+        return ids
+
+    def batch_search(self, queries, topk, ef=100, num_threads=1, out=None):
+        q = _f32(queries)
+        ids = out if out is not None else np.zeros((q.shape[0], topk), np.uint32)
+        check(lib().ab_index_batch_search(self.h, _p(q, f32p), C.c_uint64(q.shape[0]), C.c_uint32(topk), C.c_uint32(ef), C.c_uint32(num_threads), _p(ids, u32p)))
+        return ids
+
+    def batch_search_ptr(self, q_ptr, nq, topk, ef, ids_ptr):
+        """Host pointers (e.g. pinned torch tensors); no numpy on the path."""
+        check(lib().ab_index_batch_search(self.h, C.cast(_vp(q_ptr), f32p), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef), C.c_uint32(1), C.cast(_vp(ids_ptr), u32p)))
+
+    def batch_search_with_distance(self, queries, topk, ef=100, num_threads=1):
+        q = _f32(queries)
+        ids = np.zeros((q.shape[0], topk), np.uint32)
+        dist = np.zeros((q.shape[0], topk), np.float32)
+        has = C.c_int32(0)
+        check(lib().ab_index_batch_search_with_distance(self.h, _p(q, f32p), C.c_uint64(q.shape[0]), C.c_uint32(topk), C.c_uint32(ef), C.c_uint32(num_threads),
+                                                        _p(ids, u32p), _p(dist, f32p), C.byref(has)))
+        return ids, (dist if has.value else np.zeros((0, topk), np.float32))
+
+    def batch_search_device(self, d_queries, nq, topk, ef, d_out_ids, d_out_dist=None, rerank=True, stream=None):
+        check(lib().ab_index_batch_search_device(self.h, _vp(d_queries), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef), C.c_int32(int(rerank)),
+                                                 _vp(d_out_ids), _vp(d_out_dist), _vp(stream)))
+
+    def traverse(self, queries, ef):
+        q = _f32(queries)
+        nq = q.shape[0]
+        ids = np.zeros((nq, ef), np.uint32)
+        dist = np.zeros((nq, ef), np.float32)
+        sizes = np.zeros(nq, np.uint32)
+        check(lib().ab_index_batch_traverse(self.h, _p(q, f32p), C.c_uint64(nq), C.c_uint32(ef), _p(ids, u32p), _p(dist, f32p), _p(sizes, u32p)))
+        return ids, dist, sizes
+
+    def stats(self):
+        st = (C.c_uint64 * 5)()
+        check(lib().ab_index_search_stats(self.h, st))
+        return dict(ndc=int(st[0]), hops=int(st[1]), overlay=int(st[2]), spilled=int(st[3]), queries=int(st[4]))
+
+    def insert(self, vec, ef=100):
+        v = _f32(vec)
+        out = C.c_uint32(0)
+        check(lib().ab_index_insert(self.h, _p(v, f32p), C.c_uint32(ef), C.byref(out)))
+        return -1 if out.value == 0xFFFFFFFF else int(out.value)
+
+    def remove(self, vid):
+        check(lib().ab_index_remove(self.h, C.c_uint32(vid)))
+
+    def save(self, index_path, data_path, quant_path=""):
+        check(lib().ab_index_save(self.h, index_path.encode(), data_path.encode(), quant_path.encode()))
+
+    def load(self, index_path, data_path, quant_path=""):
+        check(lib().ab_index_load(self.h, index_path.encode(), data_path.encode(), quant_path.encode()))
+
+
+def distance_pairs(metric, quant, x, y, mn=None, mx=None, dim=None):
+    if QUANTS[quant] == 0:
+        x, y = _f32(x), _f32(y)
+        dim = x.shape[1]
+    else:
+        x, y = np.ascontiguousarray(x, np.uint8), np.ascontiguousarray(y, np.uint8)
+        mn, mx = _f32(mn), _f32(mx)
+        dim = mn.shape[0] if dim is None else dim
+    out = np.zeros(x.shape[0], np.float32)
+    check(lib().ab_distance_pairs(C.c_int32(METRICS[metric]), C.c_int32(QUANTS[quant]), _vp(x.ctypes.data), _vp(y.ctypes.data), C.c_uint64(x.shape[0]),
+                                  C.c_uint32(dim), _p(mn, f32p) if mn is not None else None, _p(mx, f32p) if mx is not None else None, _p(out, f32p)))
+    return out
+
+
+def quant_fit_encode(quant, data):
+    d = _f32(data)
+    n, dim = d.shape
+    rb = dim if quant == "sq8" else (dim + 1) // 2
+    mn, mx = np.zeros(dim, np.float32), np.zeros(dim, np.float32)
+    codes = np.zeros((n, rb), np.uint8)
+    check(lib().ab_quant_fit_encode(C.c_int32(QUANTS[quant]), _p(d, f32p), C.c_uint64(n), C.c_uint32(dim), _p(mn, f32p), _p(mx, f32p), _p(codes, u8p)))
+    return mn, mx, codes
+
+
+def normalize_rows(data):
+    d = _f32(data).copy()
+    check(lib().ab_normalize_rows(_p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1])))
+    return d
+
+
+def bruteforce_topk(metric, data, queries, k):
+    d, q = _f32(data), _f32(queries)
+    ids = np.zeros((q.shape[0], k), np.uint32)
+    dist = np.zeros((q.shape[0], k), np.float32)
+    check(lib().ab_bruteforce_topk(C.c_int32(METRICS[metric]), _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]), _p(q, f32p),
+                                   C.c_uint64(q.shape[0]), C.c_uint32(k), _p(ids, u32p), _p(dist, f32p)))
+    return ids, dist
+
+
+def bruteforce_topk_device(metric, d_data, n, dim, d_queries, nq, k, d_out_ids, d_out_dist=None, stream=None):
+    check(lib().ab_bruteforce_topk_device(C.c_int32(METRICS[metric]), _vp(d_data), C.c_uint64(n), C.c_uint32(dim), _vp(d_queries), C.c_uint64(nq),
+                                          C.c_uint32(k), _vp(d_out_ids), _vp(d_out_dist), _vp(stream)))
+
+
+def merge_topk_device(d_dist, d_ids, lists, nq, k, d_out_ids, d_out_dist=None, stream=None):
+    check(lib().ab_merge_topk_device(_vp(d_dist), _vp(d_ids), C.c_uint32(lists), C.c_uint64(nq), C.c_uint32(k), _vp(d_out_ids), _vp(d_out_dist), _vp(stream)))

@@ -1,0 +1,245 @@
+// Exact brute-force top-k (ground truth) and the k-way merge used by sharded search.
+//
+// Replaces (paths relative to /root/reference):
+//   find_exact_gt      include/utils/evaluate.hpp:30-62   (fp32 L2 against every row + full sort)
+//   calc_gt (Python)   python/src/alayalite/utils.py:99-105
+//
+// This file is the exact fp32 path: a register-tiled distance tile (64 queries x 64 rows per CTA
+// step, difference form sum (q-x)^2 accumulated with FMAs in dimension order, like the reference's
+// scalar kernel) feeding a threshold-filtered per-query top-k kept sorted by (distance, id) in
+// shared memory. Base rows are split across CTAs in y; partial lists are merged by merge_topk.
+// The tcgen05 tensor-core filter that sits in front of it for large batches lives in
+// bruteforce_tc.cu.
+#include <cfloat>
+
+#include "kernels.cuh"
+
+namespace ab {
+
+namespace {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int TQ = 64, TB = 64, KC = 16, BF_THREADS = 256;
+
+// sorted top-k by (dist, id); warp-collective insert, arguments warp-uniform
+__device__ __forceinline__ bool pair_less(float d1, uint32_t i1, float d2, uint32_t i2) {
+  return d1 < d2 || (d1 == d2 && i1 < i2);
+}
+__device__ __forceinline__ void topk_insert(float *td, uint32_t *ti, int &size, int k, float d, uint32_t id, int lane) {
+  if (size == k && !pair_less(d, id, td[k - 1], ti[k - 1])) return;
+  int pos = 0;
+  for (int base = 0; base < size; base += 32) {
+    const int i = base + lane;
+    const uint32_t b = __ballot_sync(kFull, i < size && pair_less(td[i], ti[i], d, id));
+    pos += __popc(b);
+    if (b != kFull) break;
+  }
+  const int nsize = min(size + 1, k);
+  for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 > pos; base -= 32) {
+    const int i = base + lane;
+    const bool mv = i > pos && i < nsize;
+    float xd = 0.f;
+    uint32_t xi = 0;
+    if (mv) {
+      xd = td[i - 1];
+      xi = ti[i - 1];
+    }
+    __syncwarp();
+    if (mv) {
+      td[i] = xd;
+      ti[i] = xi;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    td[pos] = d;
+    ti[pos] = id;
+  }
+  __syncwarp();
+  size = nsize;
+}
+
+template <bool IP>
+__global__ void __launch_bounds__(BF_THREADS) bf_tile_kernel(const float *__restrict__ rows, uint64_t n, uint32_t stride,
+                                                             const float *__restrict__ queries, uint64_t nq,
+                                                             uint32_t qstride, uint32_t k, uint32_t splits,
+                                                             float *__restrict__ part_dist, uint32_t *__restrict__ part_ids) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float(*Qs)[TQ + 4] = reinterpret_cast<float(*)[TQ + 4]>(smem);
+  float(*Xs)[TB + 4] = reinterpret_cast<float(*)[TB + 4]>(smem + sizeof(float) * KC * (TQ + 4));
+  uint8_t *p = smem + sizeof(float) * KC * (TQ + 4 + TB + 4);
+  float *thr = reinterpret_cast<float *>(p);            p += TQ * 4;
+  int *bcnt = reinterpret_cast<int *>(p);               p += TQ * 4;
+  int *tsize = reinterpret_cast<int *>(p);              p += TQ * 4;
+  float *bd = reinterpret_cast<float *>(p);             p += TQ * TB * 4;
+  uint32_t *bi = reinterpret_cast<uint32_t *>(p);       p += TQ * TB * 4;
+  float *td = reinterpret_cast<float *>(p);             p += size_t(TQ) * k * 4;
+  uint32_t *ti = reinterpret_cast<uint32_t *>(p);
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int ty = t / 16, tx = t % 16;
+  const uint64_t q0 = uint64_t(blockIdx.x) * TQ;
+  const uint32_t split = blockIdx.y;
+  const uint64_t rows_per = ((n + splits - 1) / splits + TB - 1) / TB * TB;
+  const uint64_t r_begin = uint64_t(split) * rows_per;
+  const uint64_t r_end = min(n, r_begin + rows_per);
+
+  for (int i = t; i < TQ; i += BF_THREADS) {
+    thr[i] = FLT_MAX;
+    bcnt[i] = 0;
+    tsize[i] = 0;
+  }
+  __syncthreads();
+
+  const int lrow = t / 4, lk = (t % 4) * 4;  // loader mapping: 64 rows x 4 float4 per K chunk
+  for (uint64_t r0 = r_begin; r0 < r_end; r0 += TB) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+    for (uint32_t kk = 0; kk < stride; kk += KC) {
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), xv = qv;
+      if (q0 + lrow < nq) qv = *reinterpret_cast<const float4 *>(queries + (q0 + lrow) * qstride + kk + lk);
+      if (r0 + lrow < r_end) xv = *reinterpret_cast<const float4 *>(rows + (r0 + lrow) * stride + kk + lk);
+      __syncthreads();
+      Qs[lk + 0][lrow] = qv.x; Qs[lk + 1][lrow] = qv.y; Qs[lk + 2][lrow] = qv.z; Qs[lk + 3][lrow] = qv.w;
+      Xs[lk + 0][lrow] = xv.x; Xs[lk + 1][lrow] = xv.y; Xs[lk + 2][lrow] = xv.z; Xs[lk + 3][lrow] = xv.w;
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < KC; c++) {
+        const float4 q4 = *reinterpret_cast<const float4 *>(&Qs[c][ty * 4]);
+        const float4 x4 = *reinterpret_cast<const float4 *>(&Xs[c][tx * 4]);
+        const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float xa[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (IP) {
+              acc[i][j] = fmaf(qa[i], xa[j], acc[i][j]);
+            } else {
+              const float df = qa[i] - xa[j];
+              acc[i][j] = fmaf(df, df, acc[i][j]);
+            }
+          }
+      }
+    }
+    // threshold filter into the per-query buffers (at most TB entries per query per tile)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int ql = ty * 4 + i;
+      const float th = thr[ql];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint64_t r = r0 + tx * 4 + j;
+        const float d = IP ? -acc[i][j] : acc[i][j];
+        if (r < r_end && q0 + ql < nq && d <= th) {
+          const int pos = atomicAdd(&bcnt[ql], 1);
+          bd[ql * TB + pos] = d;
+          bi[ql * TB + pos] = static_cast<uint32_t>(r);
+        }
+      }
+    }
+    __syncthreads();
+    // each warp folds the buffers of its 8 queries into their sorted lists
+    for (int ql = warp; ql < TQ; ql += BF_THREADS / 32) {
+      const int cnt = bcnt[ql];
+      if (cnt == 0) continue;
+      int size = tsize[ql];
+      float *qd = td + size_t(ql) * k;
+      uint32_t *qi = ti + size_t(ql) * k;
+      for (int c = 0; c < cnt; c++) topk_insert(qd, qi, size, k, bd[ql * TB + c], bi[ql * TB + c], lane);
+      if (lane == 0) {
+        tsize[ql] = size;
+        bcnt[ql] = 0;
+        if (size == static_cast<int>(k)) thr[ql] = qd[k - 1];
+      }
+    }
+    __syncthreads();
+  }
+  // partial lists: [split][nq][k]; missing entries carry FLT_MAX / id 0xFFFFFFFF
+  for (int ql = warp; ql < TQ; ql += BF_THREADS / 32) {
+    if (q0 + ql >= nq) continue;
+    const int size = tsize[ql];
+    for (uint32_t i = lane; i < k; i += 32) {
+      const size_t o = (size_t(split) * nq + q0 + ql) * k + i;
+      part_dist[o] = i < static_cast<uint32_t>(size) ? td[size_t(ql) * k + i] : FLT_MAX;
+      part_ids[o] = i < static_cast<uint32_t>(size) ? ti[size_t(ql) * k + i] : kEmptyId;
+    }
+  }
+}
+
+// one warp per query: fold `lists` sorted lists of k into one, by (dist, id)
+__global__ void __launch_bounds__(128) merge_kernel(const float *__restrict__ dist, const uint32_t *__restrict__ ids,
+                                                    uint32_t lists, uint64_t nq, uint32_t k, uint32_t *__restrict__ out_ids,
+                                                    float *__restrict__ out_dist) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  float *td = reinterpret_cast<float *>(smem) + size_t(warp) * k * 2;
+  uint32_t *ti = reinterpret_cast<uint32_t *>(td + k);
+  for (uint64_t q = uint64_t(blockIdx.x) * warps + warp; q < nq; q += uint64_t(gridDim.x) * warps) {
+    int size = 0;
+    for (uint32_t l = 0; l < lists; l++) {
+      const size_t o = (size_t(l) * nq + q) * k;
+      for (uint32_t i = 0; i < k; i++) {
+        const uint32_t id = ids[o + i];
+        if (id == kEmptyId) break;  // lists are sorted with the empty slots last
+        const float d = dist[o + i];
+        if (size == static_cast<int>(k) && !pair_less(d, id, td[k - 1], ti[k - 1])) break;  // sorted: rest is worse
+        topk_insert(td, ti, size, k, d, id, lane);
+      }
+    }
+    // slots that no shard could fill stay 0 like the reference's zero-initialised pool
+    for (uint32_t i = lane; i < k; i += 32) {
+      out_ids[q * k + i] = i < static_cast<uint32_t>(size) ? ti[i] : 0u;
+      if (out_dist) out_dist[q * k + i] = i < static_cast<uint32_t>(size) ? td[i] : 0.f;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+void merge_topk(const float *d_dist, const uint32_t *d_ids, uint32_t lists, uint64_t nq, uint32_t k, uint32_t *d_out_ids,
+                float *d_out_dist, int sm_count, cudaStream_t s) {
+  if (nq == 0) return;
+  const int warps = 4;
+  const size_t smem = size_t(warps) * k * 8;
+  const int blocks = static_cast<int>(std::min<uint64_t>((nq + warps - 1) / warps, uint64_t(sm_count) * 8));
+  AB_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  merge_kernel<<<blocks, warps * 32, smem, s>>>(d_dist, d_ids, lists, nq, k, d_out_ids, d_out_dist);
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void bruteforce_topk(int metric, const float *d_rows, uint64_t n, uint32_t stride, const float *d_queries, uint64_t nq,
+                     uint32_t qstride, uint32_t k, uint32_t *d_out_ids, float *d_out_dist, int sm_count, cudaStream_t s) {
+  if (nq == 0) return;
+  AB_CHECK(k >= 1 && k <= 256, AB_ERR_INVALID, "bruteforce_topk: k must be in [1, 256]");
+  AB_CHECK(stride % KC == 0 && qstride % KC == 0, AB_ERR_INVALID, "bruteforce_topk: rows must be padded to 16 floats");
+  const uint32_t qtiles = static_cast<uint32_t>((nq + TQ - 1) / TQ);
+  uint32_t splits = std::max<uint32_t>(1, (uint32_t(sm_count) * 3 + qtiles - 1) / qtiles);
+  const uint32_t max_splits = static_cast<uint32_t>(std::max<uint64_t>(1, (n + TB * 8 - 1) / (TB * 8)));
+  splits = std::min(splits, max_splits);
+  const size_t smem = sizeof(float) * KC * (TQ + 4 + TB + 4) + TQ * 12 + size_t(TQ) * TB * 8 + size_t(TQ) * k * 8;
+  DevBuf<float> pd;
+  DevBuf<uint32_t> pi;
+  pd.reserve(size_t(splits) * nq * k);
+  pi.reserve(size_t(splits) * nq * k);
+  const dim3 grid(qtiles, splits);
+  if (metric != AB_METRIC_L2) {
+    AB_CUDA(cudaFuncSetAttribute(bf_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    bf_tile_kernel<true><<<grid, BF_THREADS, smem, s>>>(d_rows, n, stride, d_queries, nq, qstride, k, splits, pd.p, pi.p);
+  } else {
+    AB_CUDA(cudaFuncSetAttribute(bf_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    bf_tile_kernel<false><<<grid, BF_THREADS, smem, s>>>(d_rows, n, stride, d_queries, nq, qstride, k, splits, pd.p, pi.p);
+  }
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+  merge_topk(pd.p, pi.p, splits, nq, k, d_out_ids, d_out_dist, sm_count, s);
+  AB_CUDA(cudaStreamSynchronize(s));  // partial buffers are freed on return
+}
+
+}  // namespace ab

@@ -1,0 +1,181 @@
+// Device distance evaluation for the raw / SQ8 / SQ4 spaces.
+//
+// Replaces the reference's host SIMD kernels (paths relative to /root/reference):
+//   simd::l2_sqr / ip_sqr            include/simd/distance_l2.ipp:41-181, distance_ip.ipp:45-170
+//   simd::l2_sqr_sq8 / ip_sqr_sq8    distance_l2.ipp:187-408,  distance_ip.ipp:177-375
+//   simd::l2_sqr_sq4 / ip_sqr_sq4    distance_l2.ipp:209-237,:413-676, distance_ip.ipp:380-686
+//
+// Layout: a row (vector or code string) is a sequence of 16-byte chunks; rows start on 64-byte
+// boundaries (the reference's SequentialStorage stride) and are zero padded. A sub-warp of TPV
+// lanes owns one candidate row: lane l reads chunks l, l+TPV, ... with 128-bit loads, accumulates
+// its partial sum in fp32 with FMAs, and the partials are combined by an xor-butterfly.
+// The query side lives in shared memory (raw floats or codes) next to per-dimension dequantisation
+// tables (scale = (max-min)/levels, min), which are zero for padded dimensions so that padding
+// never contributes.
+//
+// SQ4 nibble pairing follows the reference *distance kernels*, not its encoder: within byte j the
+// LOW nibble is scored with table entry 2j and the HIGH nibble with entry 2j+1, although the
+// encoder stored dimension 2j in the high nibble. Results parity
+// requires reproducing that.
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+struct QuerySmem {
+  const float *q_raw;     // raw query, padded to a whole number of chunks (may be null for SQ traversal)
+  const uint8_t *q_code;  // encoded query (SQ only)
+  const float *scale;     // [table_len] per-dimension (max-min)*(1/levels), 0 in the padding
+  const float *vmin;      // [table_len] per-dimension min, 0 in the padding (IP only)
+};
+
+// exact uint8 -> float without I2F: place the byte in the mantissa of 2^23
+__device__ __forceinline__ float byte_as_magic(uint32_t w, int k) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + k));
+}
+constexpr float kMagic = 8388608.0f;
+
+template <bool IP>
+__device__ __forceinline__ float raw_chunk(uint4 c, int chunk, const float *q_raw, float acc) {
+  const float4 q = reinterpret_cast<const float4 *>(q_raw)[chunk];
+  const float x0 = __uint_as_float(c.x), x1 = __uint_as_float(c.y), x2 = __uint_as_float(c.z),
+              x3 = __uint_as_float(c.w);
+  if (IP) {
+    acc = fmaf(q.x, x0, acc);
+    acc = fmaf(q.y, x1, acc);
+    acc = fmaf(q.z, x2, acc);
+    acc = fmaf(q.w, x3, acc);
+  } else {
+    float d0 = q.x - x0, d1 = q.y - x1, d2 = q.z - x2, d3 = q.w - x3;
+    acc = fmaf(d0, d0, acc);
+    acc = fmaf(d1, d1, acc);
+    acc = fmaf(d2, d2, acc);
+    acc = fmaf(d3, d3, acc);
+  }
+  return acc;
+}
+
+// one 32-bit word = 4 codes, table entries t[0..3]
+template <bool IP>
+__device__ __forceinline__ float sq_word(uint32_t cw, uint32_t qw, const float4 s, const float4 m, float acc) {
+  const float sv[4] = {s.x, s.y, s.z, s.w};
+  const float mv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float fc = byte_as_magic(cw, k), fq = byte_as_magic(qw, k);
+    if (IP) {
+      // -(sum (min + cq*s) * (min + cc*s))   distance_ip.ipp:177-191
+      const float xv = fmaf(fq - kMagic, sv[k], mv[k]);
+      const float yv = fmaf(fc - kMagic, sv[k], mv[k]);
+      acc = fmaf(xv, yv, acc);
+    } else {
+      // sum ((cq - cc) * s)^2                 distance_l2.ipp:187-201
+      const float sd = (fq - fc) * sv[k];
+      acc = fmaf(sd, sd, acc);
+    }
+  }
+  return acc;
+}
+
+template <bool IP>
+__device__ __forceinline__ float sq8_chunk(uint4 c, int chunk, const QuerySmem &qs, float acc) {
+  const uint4 q = reinterpret_cast<const uint4 *>(qs.q_code)[chunk];
+  const float4 *s = reinterpret_cast<const float4 *>(qs.scale) + chunk * 4;
+  const float4 *m = reinterpret_cast<const float4 *>(qs.vmin) + chunk * 4;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  acc = sq_word<IP>(c.x, q.x, s[0], IP ? m[0] : z, acc);
+  acc = sq_word<IP>(c.y, q.y, s[1], IP ? m[1] : z, acc);
+  acc = sq_word<IP>(c.z, q.z, s[2], IP ? m[2] : z, acc);
+  acc = sq_word<IP>(c.w, q.w, s[3], IP ? m[3] : z, acc);
+  return acc;
+}
+
+// one 32-bit word = 4 bytes = 8 codes; table entries 8w .. 8w+7 in the order lo0,hi0,lo1,hi1,...
+template <bool IP>
+__device__ __forceinline__ float sq4_word(uint32_t cw, uint32_t qw, const float4 *s, const float4 *m, float acc) {
+  const uint32_t clo = cw & 0x0F0F0F0Fu, chi = (cw >> 4) & 0x0F0F0F0Fu;
+  const uint32_t qlo = qw & 0x0F0F0F0Fu, qhi = (qw >> 4) & 0x0F0F0F0Fu;
+  const float4 s0 = s[0], s1 = s[1];
+  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  float mv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (IP) {
+    const float4 m0 = m[0], m1 = m[1];
+    mv[0] = m0.x; mv[1] = m0.y; mv[2] = m0.z; mv[3] = m0.w;
+    mv[4] = m1.x; mv[5] = m1.y; mv[6] = m1.z; mv[7] = m1.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float fc = byte_as_magic(h ? chi : clo, k), fq = byte_as_magic(h ? qhi : qlo, k);
+      const int t = 2 * k + h;
+      if (IP) {
+        const float xv = fmaf(fq - kMagic, sv[t], mv[t]);
+        const float yv = fmaf(fc - kMagic, sv[t], mv[t]);
+        acc = fmaf(xv, yv, acc);
+      } else {
+        const float sd = (fq - fc) * sv[t];
+        acc = fmaf(sd, sd, acc);
+      }
+    }
+  }
+  return acc;
+}
+
+template <bool IP>
+__device__ __forceinline__ float sq4_chunk(uint4 c, int chunk, const QuerySmem &qs, float acc) {
+  const uint4 q = reinterpret_cast<const uint4 *>(qs.q_code)[chunk];
+  const float4 *s = reinterpret_cast<const float4 *>(qs.scale) + chunk * 8;
+  const float4 *m = reinterpret_cast<const float4 *>(qs.vmin) + chunk * 8;
+  acc = sq4_word<IP>(c.x, q.x, s + 0, m + 0, acc);
+  acc = sq4_word<IP>(c.y, q.y, s + 2, m + 2, acc);
+  acc = sq4_word<IP>(c.z, q.z, s + 4, m + 4, acc);
+  acc = sq4_word<IP>(c.w, q.w, s + 6, m + 6, acc);
+  return acc;
+}
+
+template <int QUANT, bool IP>
+__device__ __forceinline__ float chunk_term(uint4 c, int chunk, const QuerySmem &qs, float acc) {
+  if (QUANT == AB_QUANT_NONE) return raw_chunk<IP>(c, chunk, qs.q_raw, acc);
+  if (QUANT == AB_QUANT_SQ8) return sq8_chunk<IP>(c, chunk, qs, acc);
+  return sq4_chunk<IP>(c, chunk, qs, acc);
+}
+
+// Partial distance of one row for this lane of a TPV-wide group, then group reduction.
+// Every lane of the group returns the full value. `row` may be any address when !active.
+template <int QUANT, bool IP, int TPV, int MAXC>
+__device__ __forceinline__ float row_distance(const uint8_t *row, int nchunks, int lane_in_group,
+                                              const QuerySmem &qs, bool active) {
+  uint4 c[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    const int ch = lane_in_group + i * TPV;
+    c[i] = (active && ch < nchunks) ? ldg128(row + size_t(ch) * 16) : make_uint4(0, 0, 0, 0);
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; i++) {
+    const int ch = lane_in_group + i * TPV;
+    if (active && ch < nchunks) acc = chunk_term<QUANT, IP>(c[i], ch, qs, acc);
+  }
+  // rows longer than MAXC*TPV chunks: stream the remainder
+  for (int ch = lane_in_group + MAXC * TPV; ch < nchunks; ch += TPV) {
+    if (active) acc = chunk_term<QUANT, IP>(ldg128(row + size_t(ch) * 16), ch, qs, acc);
+  }
+#pragma unroll
+  for (int o = TPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  return IP ? -acc : acc;
+}
+
+// ---- quantizer (include/space/quant/sq8.hpp:120-132, sq4.hpp:120-132) --------------------------
+// IEEE round-to-nearest sub / div / mul with no contraction, then truncation, so that codes equal
+// the host's static_cast<uint8_t>(((float)v - min) / (max - min) * levels).
+__device__ __forceinline__ uint32_t sq_quantize(float v, float mn, float mx, float levels) {
+  if (mx == mn) return 0u;
+  if (v >= mx) return static_cast<uint32_t>(levels);
+  if (v <= mn) return 0u;
+  const float scaled = __fdiv_rn(__fsub_rn(v, mn), __fsub_rn(mx, mn));
+  return static_cast<uint32_t>(__fmul_rn(scaled, levels)) & 0xFFu;
+}
+
+}  // namespace ab

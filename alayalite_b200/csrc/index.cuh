@@ -1,0 +1,86 @@
+// Device-resident index object behind the C ABI (index.cu, io.cu, build.cu, update.cu).
+#pragma once
+#include <mutex>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "common.cuh"
+#include "search.cuh"
+
+struct ab_index {
+  ab_params params{};
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_limit = 227 * 1024;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+
+  // ---- spaces (device) -----------------------------------------------------------------------
+  uint32_t dim = 0;
+  uint64_t n = 0;         // rows in the search space (grows with insert)
+  uint64_t n_raw = 0;     // rows in the raw space (== n unless quantised + inserted, reference quirk)
+  uint64_t capacity = 0;
+  uint32_t raw_stride = 0;   // floats per raw row (64-byte multiple)
+  uint32_t code_stride = 0;  // bytes per code row (64-byte multiple)
+  uint32_t row_bytes = 0;    // code bytes that carry data
+  int raw_chunks = 0, code_chunks = 0, table_len = 0;
+  ab::DevBuf<float> raw;          // [capacity, raw_stride]
+  ab::DevBuf<uint8_t> codes;      // [capacity, code_stride]
+  ab::DevBuf<float> qmin, qmax;   // [dim]
+  ab::DevBuf<float> scale, vmin;  // [table_len]
+  ab::DevBuf<uint32_t> valid;     // raw-space validity bitmap words (allocated on first remove)
+  bool has_removed = false;
+  uint32_t delete_cnt_raw = 0, delete_cnt_space = 0;  // RawSpace / SQ space delete_cnt_ (raw_space.hpp:69)
+
+  // ---- graph (device) --------------------------------------------------------------------------
+  ab::DevBuf<uint32_t> adj;       // [capacity, 32]
+  ab::DevBuf<uint32_t> ov_off;    // [capacity]
+  ab::DevBuf<uint32_t> ov_lists;  // [ov_rows, 32]
+  uint64_t ov_rows = 0;
+  uint32_t ep = 0, ep_level = 0;
+  bool has_graph = false, has_overlay = false;
+  std::vector<uint32_t> h_levels;  // host copy of the overlay levels (save / get_graph)
+
+  // ---- update context (reference: include/executor/jobs/job_context.hpp:25-29) -----------------
+  std::unordered_map<uint32_t, std::vector<uint32_t>> inserted_edges;
+  std::unordered_set<uint32_t> removed_vertices;
+  std::unordered_map<uint32_t, std::vector<uint32_t>> removed_node_nbrs;
+  std::vector<uint8_t> h_valid_raw;    // validity of the raw space rows (host mirror, for save)
+  std::vector<uint8_t> h_valid_space;  // validity of the search space rows (SQ) / same as raw
+  std::vector<uint8_t> h_valid_graph;  // validity of graph rows
+
+  // ---- search workspace ------------------------------------------------------------------------
+  ab::DevBuf<float> w_queries;
+  ab::DevBuf<uint32_t> w_ids, w_cand;
+  ab::DevBuf<float> w_dist;
+  ab::DevBuf<uint32_t> w_pool_ids, w_pool_sizes;
+  ab::DevBuf<float> w_pool_dist;
+  ab::DevBuf<uint32_t> w_counter;            // [1]
+  ab::DevBuf<unsigned long long> w_stats;    // [4]
+  ab::DevBuf<uint32_t> w_bitmaps;
+  size_t bitmap_words = 0;
+  int bitmap_slots = 0;
+  uint64_t last_stats[5] = {0, 0, 0, 0, 0};
+};
+
+namespace ab {
+
+void index_configure_layout(ab_index *ix, uint32_t dim);
+void index_alloc_spaces(ab_index *ix);
+void index_upload_graph(ab_index *ix, const uint32_t *adj, const uint32_t *levels, const uint32_t *lists_flat,
+                        uint64_t lists_len, uint32_t ep);
+void index_download_graph(ab_index *ix, uint32_t *adj, uint32_t *levels, uint32_t *lists_flat);
+uint64_t index_lists_len(const ab_index *ix);
+// d_queries / outputs are device pointers. cand/pool outputs optional.
+void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
+                         uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
+                         uint32_t *d_pool_sizes, cudaStream_t stream);
+void index_save(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
+void index_load(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
+void index_build_graph(ab_index *ix, uint32_t ef_construction);
+uint32_t index_insert(ab_index *ix, const float *vec, uint32_t ef);
+void index_remove(ab_index *ix, uint32_t id);
+void index_sync_valid_bitmap(ab_index *ix);
+
+}  // namespace ab

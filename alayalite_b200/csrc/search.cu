@@ -1,0 +1,541 @@
+// Batched beam search over the level-0 graph (+ overlay descent) and the SQ re-rank.
+//
+// Replaces, on the device (paths relative to /root/reference):
+//   GraphSearchJob::search / search_solo   include/executor/jobs/graph_search_job.hpp:221-258, :302-335
+//   OverlayGraph::initialize               include/index/graph/overlay_graph.hpp:122-144
+//   LinearPool (insert / pop / cursor)     include/utils/query_utils.hpp:237-312
+//   DynamicBitset visited set              include/utils/query_utils.hpp:69-115
+//   Scheduler / Worker coroutine executor  include/executor/scheduler.hpp:113-203, worker.hpp:111-136
+//   PyIndex::rerank                        python/include/index.hpp:450-488
+//
+// Design. One warp owns one query at a time and pulls the next query index from a global counter
+// (the role of the reference's task queue). Per hop the warp
+//   1. pops the closest un-expanded pool entry (pool lives in shared memory, sorted, expanded flag
+//      in bit 31 of the id exactly like LinearPool),
+//   2. reads the 128-byte adjacency row with one coalesced load (lane j <- neighbour j),
+//   3. filters neighbours through the visited set: an exact open-addressing hash of ids in shared
+//      memory; when a query outgrows it, the warp spills to its private N-bit bitmap in global
+//      memory (the reference's structure) -- never a false "visited", never a false "new",
+//   4. evaluates all unvisited neighbours: sub-warps of TPV lanes each stream one candidate row with
+//      128-bit loads, up to MAXC loads in flight per lane, dequantisation fused (distance.cuh),
+//   5. inserts candidates in neighbour order with the reference's rule (reject if full and
+//      d >= worst; position = upper bound; cursor moves back if the insert lands before it).
+// Distances are plain fp32; given equal distance values the traversal is step-for-step the
+// reference's, so ids are identical up to fp32 summation-order effects.
+#include <cfloat>
+
+#include "distance.cuh"
+#include "search.cuh"
+
+namespace ab {
+
+namespace {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kR = 32;  // level-0 degree (reference: params_.max_nbrs_ is always 32 from Python)
+
+struct WarpSmem {
+  float *q_raw;       // raw query (raw space only)
+  uint8_t *q_code;    // encoded query (SQ only)
+  float *pool_d;      // [ef + 1]
+  uint32_t *pool_i;   // [ef + 1]
+  uint32_t *hash;     // [hash_size]
+  uint32_t *cand;     // [32] candidate ids of the current hop, compacted
+  float *cdist;       // [32] their distances
+};
+
+struct Visited {
+  uint32_t *hash;
+  uint32_t hmask;
+  int hshift;
+  uint32_t *bitmap;
+  bool spilled;
+};
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 0x9E3779B1u) >> shift; }
+
+// true if `key` was not yet in the set (and is now)
+__device__ __forceinline__ bool visit(const Visited &vs, uint32_t key) {
+  uint32_t slot = hash_slot(key, vs.hshift);
+  if (!vs.spilled) {
+    while (true) {
+      const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
+      if (old == kEmptyId) return true;
+      if (old == key) return false;
+      slot = (slot + 1) & vs.hmask;
+    }
+  }
+  while (true) {  // spilled: the hash is frozen (read-only), new ids go to the bitmap
+    const uint32_t cur = vs.hash[slot];
+    if (cur == key) return false;
+    if (cur == kEmptyId) break;
+    slot = (slot + 1) & vs.hmask;
+  }
+  const uint32_t bit = 1u << (key & 31);
+  const uint32_t old = atomicOr(&vs.bitmap[key >> 5], bit);
+  return (old & bit) == 0;
+}
+
+// LinearPool::insert (query_utils.hpp:254-272); warp-collective, all arguments warp-uniform.
+__device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, int &cur, int ef, float d,
+                                            uint32_t v, int lane) {
+  int pos = 0;  // upper bound: number of entries with dist <= d
+  for (int base = 0; base < size; base += 32) {
+    const int i = base + lane;
+    const uint32_t b = __ballot_sync(kFull, i < size && pd[i] <= d);
+    pos += __popc(b);
+    if (b != kFull) break;
+  }
+  const int nsize = min(size + 1, ef);
+  for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 > pos; base -= 32) {
+    const int i = base + lane;
+    const bool mv = i > pos && i < nsize;
+    float td = 0.f;
+    uint32_t ti = 0;
+    if (mv) {
+      td = pd[i - 1];
+      ti = pi[i - 1];
+    }
+    __syncwarp();
+    if (mv) {
+      pd[i] = td;
+      pi[i] = ti;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    pd[pos] = d;
+    pi[pos] = v;
+  }
+  __syncwarp();
+  size = nsize;
+  if (pos < cur) cur = pos;
+}
+
+// Evaluate the search-space distance of the candidate held by every lane with want == true.
+template <int QUANT, bool IP, int TPV, int MAXC>
+__device__ __forceinline__ float eval_lanes(const SearchArgs &a, const WarpSmem &ws, const QuerySmem &qs,
+                                            uint32_t v, bool want, int lane) {
+  constexpr int G = 32 / TPV;
+  const uint32_t mask = __ballot_sync(kFull, want);
+  const int cnt = __popc(mask);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  if (want) ws.cand[rank] = v;
+  __syncwarp();
+  const int g = lane / TPV, lg = lane % TPV;
+  for (int base = 0; base < cnt; base += G) {
+    const int k = base + g;
+    const bool act = k < cnt;
+    const uint32_t cv = act ? ws.cand[k] : 0u;
+    float d = row_distance<QUANT, IP, TPV, MAXC>(a.rows + size_t(cv) * a.row_stride, a.nchunks, lg, qs, act);
+    if (act && lg == 0) {
+      // RawSpace::QueryComputer returns FLT_MAX for tombstoned rows (raw_space.hpp:297-304)
+      if (QUANT == AB_QUANT_NONE && a.valid != nullptr && ((a.valid[cv >> 5] >> (cv & 31)) & 1u) == 0) d = FLT_MAX;
+      ws.cdist[k] = d;
+    }
+  }
+  __syncwarp();
+  const float out = want ? ws.cdist[rank] : FLT_MAX;
+  __syncwarp();
+  return out;
+}
+
+template <int QUANT, bool IP, int TPV, int MAXC>
+__global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+
+  // ---- carve shared memory: CTA-wide tables, then one region per warp -------------------------
+  float *s_scale = reinterpret_cast<float *>(smem);
+  float *s_vmin = s_scale + (QUANT != AB_QUANT_NONE ? a.table_len : 0);
+  size_t off = (QUANT != AB_QUANT_NONE ? size_t(a.table_len) * 8 : 0);
+  const size_t q_bytes = size_t(a.nchunks) * 16;
+  const size_t pool_bytes = round_up16(size_t(a.ef + 1) * 4);
+  const size_t per_warp = q_bytes + 2 * pool_bytes + size_t(a.hash_size) * 4 + 256;
+  uint8_t *wbase = smem + off + size_t(warp) * per_warp;
+  WarpSmem ws;
+  ws.q_raw = reinterpret_cast<float *>(wbase);
+  ws.q_code = wbase;
+  ws.pool_d = reinterpret_cast<float *>(wbase + q_bytes);
+  ws.pool_i = reinterpret_cast<uint32_t *>(wbase + q_bytes + pool_bytes);
+  ws.hash = reinterpret_cast<uint32_t *>(wbase + q_bytes + 2 * pool_bytes);
+  ws.cand = ws.hash + a.hash_size;
+  ws.cdist = reinterpret_cast<float *>(ws.cand + 32);
+
+  if (QUANT != AB_QUANT_NONE) {
+    for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) {
+      s_scale[i] = a.scale[i];
+      s_vmin[i] = a.vmin[i];
+    }
+    __syncthreads();
+  }
+  QuerySmem qs;
+  qs.q_raw = ws.q_raw;
+  qs.q_code = ws.q_code;
+  qs.scale = s_scale;
+  qs.vmin = s_vmin;
+
+  Visited vs;
+  vs.hash = ws.hash;
+  vs.hmask = a.hash_size - 1;
+  vs.hshift = 32 - (31 - __clz(a.hash_size));
+  vs.bitmap = a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words;
+  const uint32_t hash_limit = a.hash_size - a.hash_size / 4;  // switch to the bitmap at 3/4 load
+  const int ef = static_cast<int>(a.ef);
+
+  while (true) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(a.work_counter, 1u);
+    qi = __shfl_sync(kFull, qi, 0);
+    if (qi >= a.nq) break;
+    const float *qg = a.queries + size_t(qi) * a.dim;
+
+    // ---- stage the query -------------------------------------------------------------------
+    if (QUANT == AB_QUANT_NONE) {
+      // RawSpace::QueryComputer (raw_space.hpp:264-274): aligned copy, COS normalises first
+      const int nfl = a.nchunks * 4;
+      float ss = 0.f;
+      for (int i = lane; i < nfl; i += 32) {
+        const float x = i < static_cast<int>(a.dim) ? qg[i] : 0.f;
+        ws.q_raw[i] = x;
+        ss = fmaf(x, x, ss);
+      }
+      if (a.metric == AB_METRIC_COS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+        const float inv = static_cast<float>(1.0 / static_cast<double>(sqrtf(ss)));  // data_utils.hpp:36-46
+        __syncwarp();
+        for (int i = lane; i < nfl; i += 32) ws.q_raw[i] *= inv;
+      }
+    } else if (QUANT == AB_QUANT_SQ8) {
+      // SQ8Space::QueryComputer (sq8_space.hpp:264-269): encode the (un-normalised) query
+      const int nb = a.nchunks * 16;
+      for (int i = lane; i < nb; i += 32) {
+        uint32_t c = 0;
+        if (i < static_cast<int>(a.dim)) c = sq_quantize(qg[i], a.qmin[i], a.qmax[i], 255.f);
+        ws.q_code[i] = static_cast<uint8_t>(c);
+      }
+    } else {
+      // SQ4Space::QueryComputer (sq4_space.hpp:265-270) + SQ4Quantizer::encode (sq4.hpp:139-149)
+      const int nb = a.nchunks * 16;
+      for (int j = lane; j < nb; j += 32) {
+        uint32_t first = 0, second = 0;
+        const int i = 2 * j;
+        if (i < static_cast<int>(a.dim)) first = sq_quantize(qg[i], a.qmin[i], a.qmax[i], 15.f);
+        if (i + 1 < static_cast<int>(a.dim)) second = sq_quantize(qg[i + 1], a.qmin[i + 1], a.qmax[i + 1], 15.f);
+        ws.q_code[j] = static_cast<uint8_t>((first << 4) | second);
+      }
+    }
+    for (uint32_t i = lane; i < a.hash_size; i += 32) ws.hash[i] = kEmptyId;
+    for (int i = lane; i <= ef; i += 32) {
+      ws.pool_d[i] = 0.f;
+      ws.pool_i[i] = 0u;
+    }
+    __syncwarp();
+
+    int size = 0, cur = 0;
+    uint32_t nvis = 0;
+    unsigned long long ndc = 0, hops = 0, ndc_ov = 0;
+    vs.spilled = false;
+
+    // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
+    uint32_t u = a.ep;
+    float cur_d = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, u, lane == 0, lane);
+    cur_d = __shfl_sync(kFull, cur_d, 0);
+    ndc_ov += 1;
+    if (a.ov_off != nullptr) {
+      for (int level = static_cast<int>(a.ep_level); level > 0; --level) {
+        bool changed = true;
+        while (changed) {
+          changed = false;
+          const uint32_t row = a.ov_off[u] + static_cast<uint32_t>(level - 1);
+          const uint32_t v = a.ov_lists[size_t(row) * kR + lane];
+          const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
+          const int cnt = empties ? __ffs(empties) - 1 : kR;
+          const bool want = lane < cnt;
+          float d = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, v, want, lane);
+          ndc_ov += cnt;
+          // sequential "if (dist < cur_dist)" scan == first index attaining the minimum, if < cur_d
+          float best = want ? d : FLT_MAX;
+          int best_lane = lane;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(kFull, best, o);
+            const int ol = __shfl_xor_sync(kFull, best_lane, o);
+            if (od < best || (od == best && ol < best_lane)) {
+              best = od;
+              best_lane = ol;
+            }
+          }
+          if (cnt > 0 && best < cur_d) {
+            cur_d = best;
+            u = __shfl_sync(kFull, v, best_lane);
+            changed = true;
+          }
+        }
+      }
+    }
+    pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, cur_d, u, lane);
+    if (lane == 0) visit(vs, u);
+    nvis = 1;
+    __syncwarp();
+
+    // ---- best-first search on level 0 (graph_search_job.hpp:307-331) ---------------------------
+    while (cur < size) {
+      // LinearPool::pop (query_utils.hpp:284-293)
+      u = ws.pool_i[cur];
+      __syncwarp();
+      if (lane == 0) ws.pool_i[cur] = u | kCheckedBit;
+      __syncwarp();
+      {
+        int nxt = size;
+        for (int base = cur + 1; base < size; base += 32) {
+          const int i = base + lane;
+          const uint32_t b = __ballot_sync(kFull, i < size && (ws.pool_i[i] & kCheckedBit) == 0);
+          if (b) {
+            nxt = base + __ffs(b) - 1;
+            break;
+          }
+        }
+        cur = nxt;
+      }
+      hops++;
+
+      const uint32_t v = a.adj[size_t(u) * kR + lane];
+      const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
+      const int cnt = empties ? __ffs(empties) - 1 : kR;
+      if (!vs.spilled && nvis + kR > hash_limit) vs.spilled = true;
+      const bool is_new = lane < cnt && visit(vs, v);
+      const uint32_t newmask = __ballot_sync(kFull, is_new);
+      const int nnew = __popc(newmask);
+      if (nnew == 0) continue;
+      nvis += nnew;
+      ndc += nnew;
+      const float d = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, v, is_new, lane);
+
+      // inserts in neighbour order. A candidate that fails "d < worst" against a full pool now can
+      // only fail later too (worst never grows), so pre-filtering is exact.
+      const float worst = size == ef ? ws.pool_d[size - 1] : FLT_MAX;
+      uint32_t acc = __ballot_sync(kFull, is_new && (size < ef || d < worst));
+      while (acc) {
+        const int j = __ffs(acc) - 1;
+        acc &= acc - 1;
+        const float dj = __shfl_sync(kFull, d, j);
+        const uint32_t vj = __shfl_sync(kFull, v, j);
+        if (size == ef && dj >= ws.pool_d[size - 1]) continue;
+        pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, dj, vj, lane);
+      }
+    }
+
+    // ---- results ----------------------------------------------------------------------------
+    for (uint32_t i = lane; i < a.topk; i += 32) {
+      const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
+      a.out_ids[size_t(qi) * a.topk + i] = in ? (ws.pool_i[i] & kIdMask) : 0u;
+      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = in ? ws.pool_d[i] : 0.f;
+    }
+    if (a.pool_ids) {
+      for (int i = lane; i < ef; i += 32) {
+        a.pool_ids[size_t(qi) * a.ef + i] = i < size ? (ws.pool_i[i] & kIdMask) : 0u;
+        a.pool_dist[size_t(qi) * a.ef + i] = i < size ? ws.pool_d[i] : 0.f;
+      }
+      if (lane == 0) a.pool_sizes[qi] = size;
+    }
+    if (vs.spilled) {
+      // give the private bitmap back all-zero (the reference allocates + zeroes one per query)
+      uint4 *bm = reinterpret_cast<uint4 *>(vs.bitmap);
+      for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
+    }
+    if (lane == 0) {
+      atomicAdd(&a.stats[0], ndc);
+      atomicAdd(&a.stats[1], hops);
+      atomicAdd(&a.stats[2], ndc_ov);
+      if (vs.spilled) atomicAdd(&a.stats[3], 1ull);
+    }
+    __syncwarp();
+  }
+}
+
+// PyIndex::rerank (python/include/index.hpp:450-467): exact raw-space distance for the ef entries of
+// res_pool -- the topk ids search wrote plus (ef - topk) untouched zeros -- ordered by (dist, id).
+template <bool IP, int TPV, int MAXC>
+__global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const size_t q_bytes = size_t(a.nchunks) * 16;
+  const uint32_t nz = min(a.ef - a.topk, a.topk);  // copies of id 0 that can reach the output
+  const uint32_t L = a.topk + nz;
+  const size_t per_warp = q_bytes + round_up16(size_t(L) * 4) * 2;
+  uint8_t *wbase = smem + size_t(warp) * per_warp;
+  float *q_raw = reinterpret_cast<float *>(wbase);
+  float *ld = reinterpret_cast<float *>(wbase + q_bytes);
+  uint32_t *li = reinterpret_cast<uint32_t *>(wbase + q_bytes + round_up16(size_t(L) * 4));
+  QuerySmem qs;
+  qs.q_raw = q_raw;
+  qs.q_code = nullptr;
+  qs.scale = nullptr;
+  qs.vmin = nullptr;
+  constexpr int G = 32 / TPV;
+  const int g = lane / TPV, lg = lane % TPV;
+
+  for (uint32_t qi = blockIdx.x * warps + warp; qi < a.nq; qi += gridDim.x * warps) {
+    const float *qg = a.queries + size_t(qi) * a.dim;
+    const int nfl = a.nchunks * 4;
+    float ss = 0.f;
+    for (int i = lane; i < nfl; i += 32) {
+      const float x = i < static_cast<int>(a.dim) ? qg[i] : 0.f;
+      q_raw[i] = x;
+      ss = fmaf(x, x, ss);
+    }
+    if (a.metric == AB_METRIC_COS) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+      const float inv = static_cast<float>(1.0 / static_cast<double>(sqrtf(ss)));
+      __syncwarp();
+      for (int i = lane; i < nfl; i += 32) q_raw[i] *= inv;
+    }
+    for (uint32_t i = lane; i < L; i += 32) li[i] = i < a.topk ? a.cand_ids[size_t(qi) * a.topk + i] : 0u;
+    __syncwarp();
+    // distances of the topk candidates and of id 0 (entry topk), shared by all its copies
+    const uint32_t ndist = a.topk + (nz > 0 ? 1u : 0u);
+    for (uint32_t base = 0; base < ndist; base += G) {
+      const uint32_t k = base + g;
+      const bool act = k < ndist;
+      const uint32_t cv = act ? li[k] : 0u;
+      float d = row_distance<AB_QUANT_NONE, IP, TPV, MAXC>(reinterpret_cast<const uint8_t *>(a.raw) + size_t(cv) * a.raw_stride,
+                                                          a.nchunks, lg, qs, act);
+      if (act && lg == 0) {
+        if (a.valid != nullptr && ((a.valid[cv >> 5] >> (cv & 31)) & 1u) == 0) d = FLT_MAX;
+        ld[k] = d;
+      }
+    }
+    __syncwarp();
+    for (uint32_t i = a.topk + 1 + lane; i < L; i += 32) ld[i] = ld[a.topk];
+    __syncwarp();
+    // rank sort by (dist, id, position)
+    for (uint32_t i = lane; i < L; i += 32) {
+      const float di = ld[i];
+      const uint32_t ii = li[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < L; j++) {
+        const float dj = ld[j];
+        const uint32_t ij = li[j];
+        rank += (dj < di || (dj == di && (ij < ii || (ij == ii && j < i)))) ? 1u : 0u;
+      }
+      if (rank < a.topk) {
+        a.out_ids[size_t(qi) * a.topk + rank] = ii;
+        if (a.out_dist) a.out_dist[size_t(qi) * a.topk + rank] = di;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int pick_tpv(int nchunks) {
+  // aim for up to 8 x 128-bit loads in flight per lane
+  if (nchunks > 128) return 32;
+  if (nchunks > 64) return 16;
+  if (nchunks > 32) return 8;
+  return 4;
+}
+
+template <int QUANT, bool IP>
+void launch_search_t(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
+  const dim3 grid(p.ctas), block(p.warps_per_cta * 32);
+#define AB_LAUNCH(TPV)                                                                                          \
+  {                                                                                                             \
+    auto kern = beam_search_kernel<QUANT, IP, TPV, 8>;                                                          \
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes))); \
+    kern<<<grid, block, p.smem_bytes, s>>>(a);                                                                  \
+  }
+  switch (p.tpv) {
+    case 4: AB_LAUNCH(4); break;
+    case 8: AB_LAUNCH(8); break;
+    case 16: AB_LAUNCH(16); break;
+    default: AB_LAUNCH(32); break;
+  }
+#undef AB_LAUNCH
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace
+
+SearchPlan plan_search(int quant, int nchunks, int table_len, uint32_t dim, uint32_t ef, uint32_t nq, int sm_count,
+                       size_t smem_limit) {
+  (void)dim;
+  SearchPlan p{};
+  p.tpv = pick_tpv(nchunks);
+  uint32_t h = 512;
+  while (h < ef * 32u && h < 16384u) h <<= 1;
+  const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;
+  const size_t pool_bytes = round_up16(size_t(ef + 1) * 4);
+  auto per_warp = [&](uint32_t hs) { return size_t(nchunks) * 16 + 2 * pool_bytes + size_t(hs) * 4 + 256; };
+  // keep at least ~16 resident warps per SM: shrink the hash (queries then spill to the bitmap) if needed
+  while (h > 512 && (smem_limit - 2 * cta_fixed) / per_warp(h) < 16) h >>= 1;
+  p.hash_size = h;
+  const size_t pw = per_warp(h);
+  int warps_per_sm = static_cast<int>((smem_limit - 2 * cta_fixed - 2048) / pw);
+  warps_per_sm = std::max(1, std::min(warps_per_sm, 32));
+  // CTAs of up to 8 warps; as many CTAs per SM as fit
+  int wpc = std::min(8, warps_per_sm);
+  int ctas_per_sm = std::max(1, warps_per_sm / wpc);
+  while (ctas_per_sm * (cta_fixed + size_t(wpc) * pw + 1024) > smem_limit && ctas_per_sm > 1) ctas_per_sm--;
+  p.warps_per_cta = wpc;
+  p.smem_bytes = cta_fixed + size_t(wpc) * pw;
+  const int want_ctas = static_cast<int>((nq + wpc - 1) / wpc);
+  p.ctas = std::max(1, std::min(want_ctas, sm_count * ctas_per_sm));
+  p.slots = p.ctas * p.warps_per_cta;
+  return p;
+}
+
+void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream) {
+  const bool ip = args.metric != AB_METRIC_L2;
+  if (quant == AB_QUANT_NONE) {
+    ip ? launch_search_t<AB_QUANT_NONE, true>(plan, args, stream) : launch_search_t<AB_QUANT_NONE, false>(plan, args, stream);
+  } else if (quant == AB_QUANT_SQ8) {
+    ip ? launch_search_t<AB_QUANT_SQ8, true>(plan, args, stream) : launch_search_t<AB_QUANT_SQ8, false>(plan, args, stream);
+  } else {
+    ip ? launch_search_t<AB_QUANT_SQ4, true>(plan, args, stream) : launch_search_t<AB_QUANT_SQ4, false>(plan, args, stream);
+  }
+}
+
+void launch_rerank(const RerankArgs &a, int sm_count, cudaStream_t stream) {
+  const int tpv = pick_tpv(a.nchunks);
+  const uint32_t nz = std::min(a.ef - a.topk, a.topk);
+  const uint32_t L = a.topk + nz;
+  const int warps = 4;
+  const size_t per_warp = size_t(a.nchunks) * 16 + round_up16(size_t(L) * 4) * 2;
+  const size_t smem = per_warp * warps;
+  const int ctas = std::max(1, std::min<int>((a.nq + warps - 1) / warps, sm_count * 8));
+  const bool ip = a.metric != AB_METRIC_L2;
+#define AB_RR(IPV, TPV)                                                                                   \
+  {                                                                                                       \
+    auto kern = rerank_kernel<IPV, TPV, 8>;                                                               \
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    kern<<<ctas, warps * 32, smem, stream>>>(a);                                                          \
+  }
+  if (ip) {
+    switch (tpv) {
+      case 4: AB_RR(true, 4); break;
+      case 8: AB_RR(true, 8); break;
+      case 16: AB_RR(true, 16); break;
+      default: AB_RR(true, 32); break;
+    }
+  } else {
+    switch (tpv) {
+      case 4: AB_RR(false, 4); break;
+      case 8: AB_RR(false, 8); break;
+      case 16: AB_RR(false, 16); break;
+      default: AB_RR(false, 32); break;
+    }
+  }
+#undef AB_RR
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace ab

@@ -1,0 +1,72 @@
+// Host-visible description of one batched graph search launch (search.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+// Everything the traversal kernel reads, by value. Device pointers unless noted.
+struct SearchArgs {
+  // search space rows: raw floats or SQ codes, row stride in bytes (multiple of 64)
+  const uint8_t *rows;
+  size_t row_stride;
+  int nchunks;         // 16-byte chunks per row that carry data
+  int table_len;       // entries in the dequantisation tables (SQ only)
+  const float *qmin;   // [dim] quantizer min (SQ only)
+  const float *qmax;   // [dim] quantizer max (SQ only)
+  const float *scale;  // [table_len] (max-min)/levels, zero padded (SQ only)
+  const float *vmin;   // [table_len] min, zero padded (SQ only)
+  // graph
+  const uint32_t *adj;       // [n, 32] level-0 adjacency, 0xFFFFFFFF padded, compact from the left
+  const uint32_t *ov_off;    // [n] first overlay row of a node (rows of 32 ids), 0xFFFFFFFF = level 0; null = no overlay
+  const uint32_t *ov_lists;  // overlay rows
+  const uint32_t *valid;     // raw-space validity bitmap (null = every row valid)
+  uint32_t ep, ep_level, n, dim;
+  int metric;  // ab_metric
+  // queries
+  const float *queries;  // [nq, dim] dense
+  uint32_t nq;
+  uint32_t ef, topk;
+  // outputs: first topk pool entries (ids 0 / dist 0 past the pool size, like the reference's
+  // zero-initialised LinearPool), optional whole pools
+  uint32_t *out_ids;   // [nq, topk]
+  float *out_dist;     // [nq, topk] or null
+  uint32_t *pool_ids;  // [nq, ef] or null
+  float *pool_dist;    // [nq, ef] or null
+  uint32_t *pool_sizes;
+  // scheduling + visited set
+  uint32_t *work_counter;       // zeroed before launch
+  uint32_t hash_size;           // shared-memory hash entries per warp (power of two)
+  uint32_t *bitmaps;            // [slots, bitmap_words] all zero between launches
+  size_t bitmap_words;
+  unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, spilled queries}
+};
+
+struct RerankArgs {
+  const float *raw;  // raw rows
+  size_t raw_stride; // bytes
+  int nchunks;
+  const uint32_t *valid;
+  const float *queries;
+  uint32_t nq, dim, ef, topk;
+  int metric;
+  const uint32_t *cand_ids;  // [nq, topk] search-space top-k
+  uint32_t *out_ids;         // [nq, topk]
+  float *out_dist;           // [nq, topk] or null
+};
+
+// Launch configuration chosen on the host (search.cu)
+struct SearchPlan {
+  int tpv;            // lanes per candidate row
+  int warps_per_cta;
+  int ctas;
+  uint32_t hash_size;
+  size_t smem_bytes;
+  int slots;          // ctas * warps_per_cta (bitmap slots needed)
+};
+
+SearchPlan plan_search(int quant, int nchunks, int table_len, uint32_t dim, uint32_t ef, uint32_t nq, int sm_count,
+                       size_t smem_limit);
+void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
+void launch_rerank(const RerankArgs &args, int sm_count, cudaStream_t stream);
+
+}  // namespace ab
