@@ -1,12 +1,506 @@
-// GPU HNSW construction (placeholder until the batched builder lands in this file).
+// HNSW construction on the GPU.
+//
+// Replaces (paths relative to /root/reference):
+//   HNSWBuilder::build_graph                 include/index/graph/hnsw/hnsw_builder.hpp:98-194
+//   HNSWImpl::add_point                      include/index/graph/hnsw/hnswlib.hpp:652-751
+//   HNSWImpl::search_base_layer              hnswlib.hpp:373-489   -> beam_search_kernel at ef_construction
+//   HNSWImpl::get_neighbors_by_heuristic2    hnswlib.hpp:291-354   -> select_kernel / reverse_kernel
+//   HNSWImpl::mutually_connect_new_element   hnswlib.hpp:512-635   -> select_kernel + reverse_kernel
+//
+// The reference inserts points one at a time under per-node mutexes. Here every layer is built by
+// *batched* insertion: a batch of new points searches the graph built so far (the same traversal
+// kernel that serves queries, queries = stored rows), each point picks <= M = 16 diverse neighbours
+// with the hnswlib heuristic (keep c iff no kept r has d(r,c) < d(c,p)), and the reverse edges of
+// the whole batch are grouped by target node (radix sort) so that one warp appends to / re-prunes
+// one adjacency row without locks. Batches start at one point and grow with the graph (a quarter of
+// what is already inserted, capped) so early points see each other.
+//
+// What is kept from the reference: M = 16, M0 = 32, efc = max(efc, 16), the level of every point
+// (std::default_random_engine seeded 100, floor(-ln(U) / ln 16), drawn in id order, hnswlib.hpp:182-186),
+// the entry point (first point of maximal level), <= 16 links for a new node on every level incl. 0
+// (hnswlib.hpp:523), list caps 32 / 16 with heuristic re-pruning on overflow (:594-629), and the
+// exported layout (-1 padded rows, overlay rows of 32 slots with <= 16 used, hnsw_builder.hpp:145-192).
+// What differs: insertion order (points with upper levels first) and batch visibility, hence the
+// edges themselves; the acceptance bar is recall at equal ef, not edge identity.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cub/device/device_radix_sort.cuh>
+#include <numeric>
+#include <random>
+
+#include "distance.cuh"
 #include "index.cuh"
 
 namespace ab {
 
+namespace {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kR = 32;
+constexpr int kM = 16;           // hnswlib max_edge_num_ = R / 2
+constexpr int kMaxIncoming = 32; // reverse edges folded into one row per batch
+
+struct LayerView {
+  const uint8_t *rows;  // raw rows of this layer's id space
+  size_t stride;        // bytes
+  int nchunks;
+  uint32_t *adj;        // [m, 32]
+  uint32_t mmax;        // list cap: 32 on level 0, 16 above
+};
+
+// distances from the row staged in `qs` to rows ids[0..count) -> out[0..count); warp-collective
+template <bool IP, int TPV>
+__device__ __forceinline__ void staged_distances(const LayerView &L, const QuerySmem &qs, const uint32_t *ids, int count,
+                                                 float *out, int lane) {
+  constexpr int G = 32 / TPV;
+  const int g = lane / TPV, lg = lane % TPV;
+  for (int base = 0; base < count; base += G) {
+    const int k = base + g;
+    const bool act = k < count;
+    const uint32_t id = act ? ids[k] : 0u;
+    const float d = row_distance<AB_QUANT_NONE, IP, TPV, 8>(L.rows + size_t(id) * L.stride, L.nchunks, lg, qs, act);
+    if (act && lg == 0) out[k] = d;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void stage_row(const LayerView &L, uint32_t id, float *q, int lane) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(L.rows + size_t(id) * L.stride);
+  for (int c = lane; c < L.nchunks; c += 32) reinterpret_cast<uint4 *>(q)[c] = src[c];
+  __syncwarp();
+}
+
+// hnswlib heuristic over candidates sorted ascending by distance to the centre node:
+// keep c iff every already kept r has d(r, c) >= d(c, centre); stop at `limit` kept.
+template <bool IP, int TPV>
+__device__ __forceinline__ int heuristic(const LayerView &L, float *q, const uint32_t *cid, const float *cd, int total,
+                                         int limit, uint32_t *kept, float *kept_d, float *scratch, int lane) {
+  QuerySmem qs{q, nullptr, nullptr, nullptr};
+  int nkept = 0;
+  for (int c = 0; c < total && nkept < limit; c++) {
+    const uint32_t id = cid[c];
+    const float dc = cd[c];
+    bool bad = false;
+    if (nkept > 0) {
+      stage_row(L, id, q, lane);
+      staged_distances<IP, TPV>(L, qs, kept, nkept, scratch, lane);
+      for (int k = lane; k < nkept; k += 32) bad |= scratch[k] < dc;
+    }
+    if (!__any_sync(kFull, bad)) {
+      if (lane == 0) {
+        kept[nkept] = id;
+        kept_d[nkept] = dc;
+      }
+      nkept++;
+    }
+    __syncwarp();
+  }
+  return nkept;
+}
+
+// smem per warp: q row | kept ids[32] | kept d[32] | scratch[64] | cand id[64] | cand d[64] | sorted id[64] | sorted d[64]
+__host__ __device__ inline size_t build_warp_smem(int nchunks) { return size_t(nchunks) * 16 + (32 + 32 + 64 + 64 * 4) * 4; }
+
+// mutually_connect_new_element, first half: choose the links of every new point of the batch
+template <bool IP, int TPV>
+__global__ void __launch_bounds__(128) select_kernel(const LayerView L, const uint32_t *__restrict__ batch_ids, uint32_t B,
+                                                     const uint32_t *__restrict__ pool_ids, const float *__restrict__ pool_dist,
+                                                     const uint32_t *__restrict__ pool_sizes, uint32_t ef,
+                                                     uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ edge_src,
+                                                     float *__restrict__ edge_dist) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint8_t *wb = smem + size_t(warp) * build_warp_smem(L.nchunks);
+  float *q = reinterpret_cast<float *>(wb);
+  uint32_t *kept = reinterpret_cast<uint32_t *>(wb + size_t(L.nchunks) * 16);
+  float *kept_d = reinterpret_cast<float *>(kept + 32);
+  float *scratch = kept_d + 32;
+  for (uint32_t b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    const uint32_t p = batch_ids[b];
+    const int size = static_cast<int>(min(pool_sizes[b], ef));
+    const uint32_t *cid = pool_ids + size_t(b) * ef;
+    const float *cd = pool_dist + size_t(b) * ef;
+    int nkept;
+    if (size < kM) {  // hnswlib.hpp:297-299: fewer candidates than M -> keep all
+      for (int i = lane; i < size; i += 32) {
+        kept[i] = cid[i];
+        kept_d[i] = cd[i];
+      }
+      nkept = size;
+      __syncwarp();
+    } else {
+      nkept = heuristic<IP, TPV>(L, q, cid, cd, size, kM, kept, kept_d, scratch, lane);
+    }
+    L.adj[size_t(p) * kR + lane] = lane < nkept ? kept[lane] : kEmptyId;
+    if (lane < kM) {
+      edge_dst[size_t(b) * kM + lane] = lane < nkept ? kept[lane] : kEmptyId;
+      edge_src[size_t(b) * kM + lane] = p;
+      edge_dist[size_t(b) * kM + lane] = lane < nkept ? kept_d[lane] : 0.f;
+    }
+    __syncwarp();
+  }
+}
+
+// mutually_connect_new_element, second half: one warp per target row that received reverse edges
+template <bool IP, int TPV>
+__global__ void __launch_bounds__(128) reverse_kernel(const LayerView L, const uint32_t *__restrict__ sorted_dst,
+                                                      const uint32_t *__restrict__ sorted_idx,
+                                                      const uint32_t *__restrict__ edge_src,
+                                                      const float *__restrict__ edge_dist, uint32_t nedges) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint8_t *wb = smem + size_t(warp) * build_warp_smem(L.nchunks);
+  float *q = reinterpret_cast<float *>(wb);
+  uint32_t *kept = reinterpret_cast<uint32_t *>(wb + size_t(L.nchunks) * 16);
+  float *kept_d = reinterpret_cast<float *>(kept + 32);
+  float *scratch = kept_d + 32;
+  uint32_t *cand = reinterpret_cast<uint32_t *>(scratch + 64);
+  float *cand_d = reinterpret_cast<float *>(cand + 64);
+  uint32_t *sid = reinterpret_cast<uint32_t *>(cand_d + 64);
+  float *sd = reinterpret_cast<float *>(sid + 64);
+  QuerySmem qs{q, nullptr, nullptr, nullptr};
+
+  for (uint32_t i = blockIdx.x * warps + warp; i < nedges; i += gridDim.x * warps) {
+    const uint32_t r = sorted_dst[i];
+    if (r == kEmptyId || (i > 0 && sorted_dst[i - 1] == r)) continue;  // only segment heads work
+    const uint32_t same = __ballot_sync(kFull, i + lane < nedges && sorted_dst[i + lane] == r);
+    const int inc = min(__ffs(~same) - 1 < 0 ? 32 : __ffs(~same) - 1, kMaxIncoming);
+    uint32_t pj = 0;
+    float dj = 0.f;
+    if (lane < inc) {
+      const uint32_t e = sorted_idx[i + lane];
+      pj = edge_src[e];
+      dj = edge_dist[e];
+    }
+    const uint32_t cur = L.adj[size_t(r) * kR + lane];
+    const uint32_t empties = __ballot_sync(kFull, cur == kEmptyId);
+    const int cnt = empties ? __ffs(empties) - 1 : kR;
+    if (cnt + inc <= static_cast<int>(L.mmax)) {  // hnswlib.hpp:594-597: room left -> append
+      if (lane < inc) L.adj[size_t(r) * kR + cnt + lane] = pj;
+      continue;
+    }
+    // hnswlib.hpp:598-629: distances of the current links to r, then heuristic over links + new
+    if (lane < cnt) cand[lane] = cur;
+    if (lane < inc) {
+      cand[cnt + lane] = pj;
+      cand_d[cnt + lane] = dj;
+    }
+    stage_row(L, r, q, lane);
+    staged_distances<IP, TPV>(L, qs, cand, cnt, cand_d, lane);
+    const int total = cnt + inc;
+    for (int a = lane; a < total; a += 32) {  // rank sort by (distance, id)
+      const float da = cand_d[a];
+      const uint32_t ia = cand[a];
+      int rank = 0;
+      for (int b = 0; b < total; b++) rank += (cand_d[b] < da || (cand_d[b] == da && cand[b] < ia)) ? 1 : 0;
+      sid[rank] = ia;
+      sd[rank] = da;
+    }
+    __syncwarp();
+    const int nkept = heuristic<IP, TPV>(L, q, sid, sd, total, static_cast<int>(L.mmax), kept, kept_d, scratch, lane);
+    L.adj[size_t(r) * kR + lane] = lane < nkept ? kept[lane] : kEmptyId;
+    __syncwarp();
+  }
+}
+
+__global__ void gather_rows_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, const uint32_t *__restrict__ ids,
+                                   uint32_t m, uint32_t chunks_per_row) {
+  const uint64_t total = uint64_t(m) * chunks_per_row;
+  for (uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t r = static_cast<uint32_t>(t / chunks_per_row), c = static_cast<uint32_t>(t % chunks_per_row);
+    dst[t] = src[uint64_t(ids[r]) * chunks_per_row + c];
+  }
+}
+
+__global__ void iota_kernel(uint32_t *p, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+// local layer adjacency -> overlay rows in global ids (hnsw_builder.hpp:162-192)
+__global__ void export_overlay_kernel(const uint32_t *__restrict__ ladj, uint32_t m, const uint32_t *__restrict__ order,
+                                      const uint32_t *__restrict__ ov_off, uint32_t level, uint32_t *__restrict__ ov_lists) {
+  const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= uint64_t(m) * kR) return;
+  const uint32_t i = static_cast<uint32_t>(t / kR), j = static_cast<uint32_t>(t % kR);
+  const uint32_t v = ladj[t];
+  ov_lists[(size_t(ov_off[order[i]]) + level - 1) * kR + j] = v == kEmptyId ? kEmptyId : order[v];
+}
+
+struct Workspace {
+  DevBuf<uint32_t> pool_ids, pool_sizes, first, edge_dst, edge_src, sorted_dst, idx, sorted_idx, counter, bitmaps;
+  DevBuf<float> pool_dist, edge_dist;
+  DevBuf<unsigned long long> stats;
+  DevBuf<uint8_t> cub_tmp;
+  size_t cub_bytes = 0;
+  size_t bitmap_words = 0;
+  int slots = 0;
+};
+
+int pick_build_tpv(int nchunks) {
+  if (nchunks > 128) return 32;
+  if (nchunks > 64) return 16;
+  if (nchunks > 32) return 8;
+  return 4;
+}
+
+template <bool IP>
+void launch_select(int tpv, const LayerView &L, const uint32_t *batch_ids, uint32_t B, Workspace &w, uint32_t ef, int sms,
+                   cudaStream_t s) {
+  const int warps = 4;
+  const size_t smem = build_warp_smem(L.nchunks) * warps;
+  const int blocks = std::max(1, std::min<int>((B + warps - 1) / warps, sms * 8));
+#define AB_SEL(T)                                                                                          \
+  {                                                                                                        \
+    auto k = select_kernel<IP, T>;                                                                         \
+    AB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    k<<<blocks, warps * 32, smem, s>>>(L, batch_ids, B, w.pool_ids.p, w.pool_dist.p, w.pool_sizes.p, ef, w.edge_dst.p, \
+                                       w.edge_src.p, w.edge_dist.p);                                       \
+  }
+  switch (tpv) {
+    case 4: AB_SEL(4); break;
+    case 8: AB_SEL(8); break;
+    case 16: AB_SEL(16); break;
+    default: AB_SEL(32); break;
+  }
+#undef AB_SEL
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+template <bool IP>
+void launch_reverse(int tpv, const LayerView &L, Workspace &w, uint32_t nedges, int sms, cudaStream_t s) {
+  const int warps = 4;
+  const size_t smem = build_warp_smem(L.nchunks) * warps;
+  const int blocks = std::max(1, std::min<int>((nedges + warps - 1) / warps, sms * 16));
+#define AB_REV(T)                                                                                          \
+  {                                                                                                        \
+    auto k = reverse_kernel<IP, T>;                                                                        \
+    AB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    k<<<blocks, warps * 32, smem, s>>>(L, w.sorted_dst.p, w.sorted_idx.p, w.edge_src.p, w.edge_dist.p, nedges); \
+  }
+  switch (tpv) {
+    case 4: AB_REV(4); break;
+    case 8: AB_REV(8); break;
+    case 16: AB_REV(16); break;
+    default: AB_REV(32); break;
+  }
+#undef AB_REV
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+struct LayerJob {
+  LayerView view;
+  uint32_t m;                  // nodes in this layer's id space
+  const uint32_t *d_sequence;  // device: insertion sequence (local ids); sequence[0] is the seed
+  uint32_t total;              // entries of the sequence to insert
+  uint32_t boundary;           // sequence[1 .. boundary) search without overlay descent
+  uint32_t ep, ep_level;       // entry (local id) and its level for the descent
+  const uint32_t *ov_off, *ov_lists;  // overlay for the descent (null: none)
+};
+
+void build_layer(ab_index *ix, const LayerJob &job, uint32_t efc, uint32_t max_batch, Workspace &w, bool ip) {
+  cudaStream_t s = ix->stream;
+  const int tpv = pick_build_tpv(job.view.nchunks);
+  uint32_t inserted = 1;
+  while (inserted < job.total) {
+    uint32_t B = std::min<uint32_t>(max_batch, std::max<uint32_t>(1, inserted / 4));
+    B = std::min(B, job.total - inserted);
+    const bool descend = job.ov_off != nullptr && inserted >= job.boundary;
+    if (inserted < job.boundary) B = std::min(B, job.boundary - inserted);
+    const uint32_t *batch_ids = job.d_sequence + inserted;
+
+    // 1. candidates: the query traversal kernel at ef_construction over the graph built so far
+    SearchPlan plan = plan_search(AB_QUANT_NONE, job.view.nchunks, 0, ix->dim, efc, B, ix->sm_count, ix->smem_limit);
+    if (w.slots < plan.slots) throw Error(AB_ERR_INVALID, "build workspace: bitmap slots");
+    AB_CUDA(cudaMemsetAsync(w.counter.p, 0, sizeof(uint32_t), s));
+    SearchArgs a{};
+    a.rows = job.view.rows;
+    a.row_stride = job.view.stride;
+    a.nchunks = job.view.nchunks;
+    a.adj = job.view.adj;
+    a.ov_off = descend ? job.ov_off : nullptr;
+    a.ov_lists = job.ov_lists;
+    a.valid = nullptr;
+    a.ep = job.ep;
+    a.ep_level = descend ? job.ep_level : 0;
+    a.n = job.m;
+    a.dim = ix->dim;
+    a.metric = ip ? AB_METRIC_IP : AB_METRIC_L2;
+    a.queries = reinterpret_cast<const float *>(job.view.rows);
+    a.q_ids = batch_ids;
+    a.q_stride = job.view.stride / 4;
+    a.q_prenormalized = 1;
+    a.nq = B;
+    a.ef = efc;
+    a.topk = 1;
+    a.out_ids = w.first.p;
+    a.out_dist = nullptr;
+    a.pool_ids = w.pool_ids.p;
+    a.pool_dist = w.pool_dist.p;
+    a.pool_sizes = w.pool_sizes.p;
+    a.work_counter = w.counter.p;
+    a.hash_size = plan.hash_size;
+    a.bitmaps = w.bitmaps.p;
+    a.bitmap_words = w.bitmap_words;
+    a.stats = w.stats.p;
+    launch_search(AB_QUANT_NONE, plan, a, s);
+
+    // 2. links of the new points, 3. reverse edges grouped by target
+    const uint32_t nedges = B * kM;
+    if (ip) launch_select<true>(tpv, job.view, batch_ids, B, w, efc, ix->sm_count, s);
+    else launch_select<false>(tpv, job.view, batch_ids, B, w, efc, ix->sm_count, s);
+    AB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, w.cub_bytes, w.edge_dst.p, w.sorted_dst.p, w.idx.p, w.sorted_idx.p,
+                                            static_cast<int>(nedges), 0, 32, s));
+    count_launch(2);
+    if (ip) launch_reverse<true>(tpv, job.view, w, nedges, ix->sm_count, s);
+    else launch_reverse<false>(tpv, job.view, w, nedges, ix->sm_count, s);
+    inserted += B;
+  }
+}
+
+}  // namespace
+
 void index_build_graph(ab_index *ix, uint32_t ef_construction) {
-  (void)ix;
-  (void)ef_construction;
-  throw Error(AB_ERR_UNSUPPORTED, "GPU graph build is not implemented yet");
+  cudaStream_t s = ix->stream;
+  const uint32_t n = static_cast<uint32_t>(ix->n);
+  AB_CHECK(n > 0 && ix->n_raw == ix->n, AB_ERR_STATE, "fit the spaces first");
+  // hnsw_builder.hpp:50-51 stores efc in a uint16_t; hnswlib.hpp:101 raises it to at least M
+  const uint32_t efc = std::max<uint32_t>(static_cast<uint16_t>(ef_construction), kM);
+  AB_CHECK(efc <= 4096, AB_ERR_INVALID, "ef_construction larger than 4096 is not supported");
+  const bool ip = ix->params.metric != AB_METRIC_L2;
+
+  // ---- levels, entry point, insertion order (host) ---------------------------------------------
+  std::vector<uint32_t> levels(n);
+  {
+    std::default_random_engine gen;
+    gen.seed(100);
+    const double mult = 1 / std::log(1.0 * kM);
+    for (uint32_t i = 0; i < n; i++) {
+      std::uniform_real_distribution<double> distribution(0.0, 1.0);
+      levels[i] = static_cast<uint32_t>(static_cast<size_t>(-std::log(distribution(gen)) * mult));
+    }
+  }
+  uint32_t maxlevel = 0, ep = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (levels[i] > maxlevel) {
+      maxlevel = levels[i];
+      ep = i;
+    }
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return levels[a] > levels[b]; });
+  // order[0] == ep: the first id of maximal level. cnt[l] = number of points with level >= l.
+  std::vector<uint32_t> cnt(maxlevel + 2, 0);
+  for (uint32_t i = 0; i < n; i++)
+    for (uint32_t l = 0; l <= levels[i]; l++) cnt[l]++;
+  std::vector<uint32_t> off(ix->capacity, kEmptyId);
+  uint64_t ov_rows = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (levels[i] > 0) {
+      off[i] = static_cast<uint32_t>(ov_rows);
+      ov_rows += levels[i];
+    }
+
+  DevBuf<uint32_t> d_order, d_iota;
+  d_order.reserve(n);
+  AB_CUDA(cudaMemcpyAsync(d_order.p, order.data(), size_t(n) * 4, cudaMemcpyHostToDevice, s));
+  AB_CUDA(cudaMemcpyAsync(ix->ov_off.p, off.data(), ix->capacity * 4, cudaMemcpyHostToDevice, s));
+  ix->ov_lists.reserve(std::max<uint64_t>(ov_rows, 1) * kR);
+  AB_CUDA(cudaMemsetAsync(ix->ov_lists.p, 0xFF, std::max<uint64_t>(ov_rows, 1) * kR * 4, s));
+  AB_CUDA(cudaMemsetAsync(ix->adj.p, 0xFF, ix->capacity * kR * 4, s));
+
+  // ---- workspace ---------------------------------------------------------------------------------
+  const uint32_t max_batch = 8192;
+  Workspace w;
+  w.pool_ids.reserve(size_t(max_batch) * efc);
+  w.pool_dist.reserve(size_t(max_batch) * efc);
+  w.pool_sizes.reserve(max_batch);
+  w.first.reserve(max_batch);
+  const uint32_t max_edges = max_batch * kM;
+  w.edge_dst.reserve(max_edges);
+  w.edge_src.reserve(max_edges);
+  w.edge_dist.reserve(max_edges);
+  w.sorted_dst.reserve(max_edges);
+  w.idx.reserve(max_edges);
+  w.sorted_idx.reserve(max_edges);
+  w.counter.reserve(1);
+  w.stats.reserve(4);
+  AB_CUDA(cudaMemsetAsync(w.stats.p, 0, 32, s));
+  iota_kernel<<<(max_edges + 255) / 256, 256, 0, s>>>(w.idx.p, max_edges);
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+  AB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, w.edge_dst.p, w.sorted_dst.p, w.idx.p, w.sorted_idx.p,
+                                          static_cast<int>(max_edges), 0, 32, s));
+  w.cub_tmp.reserve(w.cub_bytes + 16);
+  SearchPlan big = plan_search(AB_QUANT_NONE, ix->raw_chunks, 0, ix->dim, efc, max_batch, ix->sm_count, ix->smem_limit);
+  w.bitmap_words = round_up((size_t(n) + 31) / 32, 4);
+  w.slots = big.slots;
+  w.bitmaps.alloc_zero(w.bitmap_words * w.slots, s);
+
+  // ---- upper layers, top down, in a compact id space (position in `order`) ------------------------
+  const uint32_t m1 = maxlevel >= 1 ? cnt[1] : 0;
+  DevBuf<uint8_t> up_rows;
+  DevBuf<uint32_t> up_adj;
+  const size_t stride = size_t(ix->raw_stride) * 4;
+  if (m1 > 1) {
+    up_rows.reserve(size_t(m1) * stride);
+    const uint32_t cpr = static_cast<uint32_t>(stride / 16);
+    gather_rows_kernel<<<std::min<uint64_t>((uint64_t(m1) * cpr + 255) / 256, 148 * 32), 256, 0, s>>>(
+        reinterpret_cast<const uint4 *>(ix->raw.p), reinterpret_cast<uint4 *>(up_rows.p), d_order.p, m1, cpr);
+    AB_CUDA(cudaGetLastError());
+    count_launch();
+    d_iota.reserve(m1);
+    iota_kernel<<<(m1 + 255) / 256, 256, 0, s>>>(d_iota.p, m1);
+    count_launch();
+    up_adj.reserve(size_t(m1) * kR);
+  }
+  for (uint32_t level = maxlevel; level >= 1; level--) {
+    const uint32_t m = cnt[level];
+    if (m <= 1) continue;  // a single node: its row stays empty
+    AB_CUDA(cudaMemsetAsync(up_adj.p, 0xFF, size_t(m) * kR * 4, s));
+    LayerJob job{};
+    job.view = LayerView{up_rows.p, stride, ix->raw_chunks, up_adj.p, kM};
+    job.m = m;
+    job.d_sequence = d_iota.p;
+    job.total = m;
+    job.boundary = m;  // no descent on upper layers: every search starts at the entry point
+    job.ep = 0;
+    job.ep_level = 0;
+    job.ov_off = nullptr;
+    job.ov_lists = nullptr;
+    build_layer(ix, job, efc, max_batch, w, ip);
+    export_overlay_kernel<<<static_cast<uint32_t>((uint64_t(m) * kR + 255) / 256), 256, 0, s>>>(up_adj.p, m, d_order.p, ix->ov_off.p,
+                                                                                               level, ix->ov_lists.p);
+    AB_CUDA(cudaGetLastError());
+    count_launch();
+  }
+
+  // ---- level 0 over all points -------------------------------------------------------------------
+  {
+    LayerJob job{};
+    job.view = LayerView{reinterpret_cast<const uint8_t *>(ix->raw.p), stride, ix->raw_chunks, ix->adj.p, kR};
+    job.m = n;
+    job.d_sequence = d_order.p;
+    job.total = n;
+    job.boundary = std::max<uint32_t>(m1, 1);  // points that live on upper layers go in first, from the entry point
+    job.ep = ep;
+    job.ep_level = maxlevel;
+    job.ov_off = maxlevel >= 1 ? ix->ov_off.p : nullptr;
+    job.ov_lists = ix->ov_lists.p;
+    build_layer(ix, job, efc, max_batch, w, ip);
+  }
+  AB_CUDA(cudaStreamSynchronize(s));
+
+  ix->ov_rows = ov_rows;
+  ix->ep = ep;
+  ix->ep_level = maxlevel;
+  ix->has_overlay = true;
+  ix->has_graph = true;
+  std::copy(levels.begin(), levels.end(), ix->h_levels.begin());
+  std::fill(ix->h_valid_graph.begin(), ix->h_valid_graph.begin() + n, 1);
 }
 
 }  // namespace ab

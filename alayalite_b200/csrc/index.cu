@@ -201,6 +201,9 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   a.dim = ix->dim;
   a.metric = ix->params.metric;
   a.queries = d_queries;
+  a.q_ids = nullptr;
+  a.q_stride = ix->dim;
+  a.q_prenormalized = 0;
   a.nq = static_cast<uint32_t>(nq);
   a.ef = ef;
   a.topk = topk;

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
     if (lane == 0) qi = atomicAdd(a.work_counter, 1u);
     qi = __shfl_sync(kFull, qi, 0);
     if (qi >= a.nq) break;
-    const float *qg = a.queries + size_t(qi) * a.dim;
+    const float *qg = a.queries + size_t(a.q_ids ? a.q_ids[qi] : qi) * a.q_stride;
 
     // ---- stage the query -------------------------------------------------------------------
     if (QUANT == AB_QUANT_NONE) {
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
         ws.q_raw[i] = x;
         ss = fmaf(x, x, ss);
       }
-      if (a.metric == AB_METRIC_COS) {
+      if (a.metric == AB_METRIC_COS && !a.q_prenormalized) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
         const float inv = static_cast<float>(1.0 / static_cast<double>(sqrtf(ss)));  // data_utils.hpp:36-46

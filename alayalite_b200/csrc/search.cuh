@@ -23,7 +23,10 @@ struct SearchArgs {
   uint32_t ep, ep_level, n, dim;
   int metric;  // ab_metric
   // queries
-  const float *queries;  // [nq, dim] dense
+  const float *queries;   // query i = queries + (q_ids ? q_ids[i] : i) * q_stride
+  const uint32_t *q_ids;  // optional indirection (graph build: the queries are base rows)
+  size_t q_stride;        // floats between consecutive query rows
+  int q_prenormalized;    // COS only: queries are stored rows, already normalised
   uint32_t nq;
   uint32_t ef, topk;
   // outputs: first topk pool entries (ids 0 / dist 0 past the pool size, like the reference's

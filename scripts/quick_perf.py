@@ -57,3 +57,23 @@ for ef in (16, 32, 50, 64, 100, 200):
     print(f"ef={ef:4d} gpu qps={nq / dt:10.0f} recall={rec(ids):.4f} ndc/q={st['ndc'] / nq:7.1f} hops/q={st['hops'] / nq:6.1f} "
           f"ov/q={st['overlay'] / nq:5.1f} B/q={bq / 1e3:7.1f}KB hbm={nq / dt * bq / 1e9:7.1f}GB/s | cpu({threads}thr solo) qps={nq / dtc:8.0f} "
           f"recall={rec(rid):.4f} same={np.mean(np.all(rid == ids, axis=1)):.3f}", flush=True)
+
+# ---- GPU-built index, same data: build time and recall at equal ef --------------------------------
+ix2 = _cabi.NativeIndex("l2", "none", n)
+t = time.time()
+ix2.fit(base, 100)
+print(f"GPU fit (spaces + graph) {time.time() - t:.2f}s", flush=True)
+g2 = ix2.graph()
+deg = (g2["adj"] != 0xFFFFFFFF).sum(1)
+degr = (g["adj"] != 0xFFFFFFFF).sum(1)
+print(f"avg level-0 degree gpu={deg.mean():.2f} ref={degr.mean():.2f}; zero-degree gpu={(deg == 0).sum()} ; ep gpu={g2['ep']} ref={g['ep']} levels equal={np.array_equal(g2['levels'], g['levels'])}")
+indeg = np.bincount(g2["adj"][g2["adj"] != 0xFFFFFFFF], minlength=n)
+print(f"unreachable (in-degree 0) gpu={(indeg == 0).sum()} ref={(np.bincount(g['adj'][g['adj'] != 0xFFFFFFFF], minlength=n) == 0).sum()}")
+for ef in (16, 32, 50, 64, 100, 200):
+    a = ix2.batch_search(q, 10, ef)
+    t = time.time()
+    a = ix2.batch_search(q, 10, ef)
+    dt = time.time() - t
+    st = ix2.stats()
+    b = ix.batch_search(q, 10, ef)
+    print(f"ef={ef:4d} recall gpu-built={rec(a):.4f} ref-built={rec(b):.4f} gpu-built qps={nq / dt:9.0f} ndc/q={st['ndc'] / nq:7.1f}", flush=True)

@@ -177,8 +177,16 @@ def test_search_sq_matches_oracle(cabi, orc, small_sets, metric, quant):
     o, ix = _pair(cabi, orc, base, metric, quant)
     mn, mx, codes = ix.codes()
     omn, omx = o.minmax()
-    assert np.array_equal(mn, omn) and np.array_equal(mx, omx)
-    assert np.array_equal(codes, o.codes())
+    if metric == "cos":
+        # rows are L2-normalised first; the reference's own normalize() is summation-order dependent
+        # (-Ofast vectorises it), so codes are pinned only up to bucket-edge flips of +-1
+        assert _close(mn, omn, rel=1e-5) and _close(mx, omx, rel=1e-5)
+        a, b = codes.astype(np.int32), o.codes().astype(np.int32)
+        diff = np.abs(a - b) if quant == "sq8" else np.maximum(np.abs((a >> 4) - (b >> 4)), np.abs((a & 15) - (b & 15)))
+        assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+    else:
+        assert np.array_equal(mn, omn) and np.array_equal(mx, omx)
+        assert np.array_equal(codes, o.codes())
     agree = []
     for ef, k in ((10, 10), (64, 10), (100, 100), (120, 7)):
         want = o.batch_search(q, k, ef)
