@@ -384,7 +384,7 @@ int ref_index_load(void *h, const char *ip, const char *dp, const char *qp) {
 }
 
 // graph accessors -----------------------------------------------------------------------------
-// info = {max_nodes, max_nbrs, ep, has_overlay, item_cnt}
+// info = {max_nodes, max_nbrs, ep, has_overlay, graph rows}
 int ref_index_graph_info(void *h, uint32_t *info) {
   auto *b = static_cast<RefIndexBase *>(h);
   auto *g = b->graph();
@@ -393,7 +393,7 @@ int ref_index_graph_info(void *h, uint32_t *info) {
   info[1] = g->max_nbrs_;
   info[2] = g->get_ep();
   info[3] = g->overlay_graph_ ? 1 : 0;
-  info[4] = b->raw() != nullptr ? b->raw()->get_data_num() : 0;
+  info[4] = static_cast<uint32_t>(g->data_storage_.pos_);  // graph rows (== search-space rows, also after inserts)
   return 0;
 }
 int ref_index_graph_rows(void *h, uint32_t first, uint32_t count, uint32_t *out) {
@@ -514,7 +514,7 @@ int ref_linear_pool_replay(uint32_t n, int capacity, const uint32_t *op_ids, con
   uint32_t np = 0;
   for (uint32_t i = 0; i < nops; i++) {
     if (op_ids[i] == 0xFFFFFFFFu) {
-      if (pool.has_next()) popped[np++] = pool.pop();
+      popped[np++] = pool.pop();
     } else {
       pool.insert(op_ids[i], op_dist[i]);
     }

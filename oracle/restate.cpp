@@ -891,7 +891,7 @@ int orc_linear_pool_replay(uint32_t n, int capacity, const uint32_t *op_ids, con
   uint32_t np = 0;
   for (uint32_t i = 0; i < nops; i++) {
     if (op_ids[i] == kEmpty) {
-      if (pool.has_next()) popped[np++] = pool.pop();
+      popped[np++] = pool.pop();  // like the reference's tests: pop() itself does not check has_next()
     } else {
       pool.insert(op_ids[i], op_dist[i]);
     }

@@ -1,0 +1,95 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every symbol the header
+declares, and every compute entry point fails loudly without a CUDA device (no CPU fallback)."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "alaya_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ab_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(cabi):
+    declared = header_symbols()
+    assert len(declared) >= 30
+    lib = cabi.lib()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(cabi.SYMBOLS) == declared  # the ctypes layer tracks the header
+
+
+def test_header_cites_the_reference_interface():
+    text = open(os.path.join(ROOT, "include", "alaya_b200.h")).read()
+    for needle in ("index.hpp:289-346", "index.hpp:177-227", "graph.hpp:165-200", "evaluate.hpp:30-62", "graph_update_job.hpp:66-89"):
+        assert needle in text
+
+
+def test_pybind_module_surface():
+    """Same names as the reference's _alayalitepy (python/src/pybind.cpp:48-147)."""
+    from alayalite_b200 import _alayalitepy as m
+
+    for name in ("IndexType", "MetricType", "QuantizationType", "IndexParams", "PyIndexInterface", "Client"):
+        assert hasattr(m, name)
+    assert {"FLAT", "HNSW", "NSG", "FUSION"} <= set(m.IndexType.__members__)
+    assert {"L2", "IP", "COS"} <= set(m.MetricType.__members__)
+    assert {"NONE", "SQ8", "SQ4", "RABITQ"} <= set(m.QuantizationType.__members__)
+    assert m.HNSW == m.IndexType.HNSW and m.L2 == m.MetricType.L2 and m.SQ8 == m.QuantizationType.SQ8  # export_values
+    p = m.IndexParams(index_type_=m.IndexType.HNSW, data_type_=np.dtype(np.float32), id_type_=np.dtype(np.uint32),
+                      quantization_type_=m.QuantizationType.NONE, metric_=m.MetricType.L2, capacity_=123)
+    assert p.capacity_ == 123 and p.metric_ == m.MetricType.L2
+    for meth in ("to_string", "fit", "search", "get_data_by_id", "insert", "remove", "batch_search", "batch_search_with_distance",
+                 "save", "load", "get_data_dim"):
+        assert hasattr(m.PyIndexInterface, meth)
+
+
+def _no_gpu(cabi):
+    return cabi.device_count() == 0
+
+
+def test_fails_loudly_without_a_gpu(cabi):
+    if not _no_gpu(cabi):
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(cabi.AbError) as e:
+        cabi.NativeIndex("l2", "none", 100)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    x = np.zeros((4, 8), np.float32)
+    for call in (lambda: cabi.bruteforce_topk("l2", x, x, 2), lambda: cabi.distance_pairs("l2", "none", x, x),
+                 lambda: cabi.quant_fit_encode("sq8", x), lambda: cabi.normalize_rows(x)):
+        with pytest.raises(cabi.AbError) as e:
+            call()
+        assert e.value.code == -2
+    from alayalite_b200 import Client, calc_gt
+
+    with pytest.raises(RuntimeError):
+        Client().create_index("x", capacity=10).fit(x)
+    with pytest.raises(RuntimeError):
+        calc_gt(x, x, 2)
+
+
+def test_bad_params_are_rejected_before_touching_the_device(cabi):
+    lib = cabi.lib()
+    h = C.c_void_p()
+    for p in (cabi.Params(0, 0, 0, 100, 32, -1),   # FLAT: "Unsupported index type" (dispatch.hpp:119-121)
+              cabi.Params(1, 7, 0, 100, 32, -1), cabi.Params(1, 0, 9, 100, 32, -1), cabi.Params(1, 0, 0, 0, 32, -1),
+              cabi.Params(1, 0, 0, 100, 64, -1)):
+        assert lib.ab_index_create(C.byref(p), C.byref(h)) < 0
+        assert lib.ab_last_error()
+    assert lib.ab_index_create(None, C.byref(h)) == -1
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under alayalite_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "alayalite_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower().replace("oracle/_ref", "").replace("the oracle", "") or f in ("synthetic.py",), f
