@@ -225,6 +225,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
     r.raw_stride = size_t(ix->raw_stride) * 4;
     r.nchunks = ix->raw_chunks;
     r.valid = ix->has_removed ? ix->valid.p : nullptr;
+    r.n_rows = static_cast<uint32_t>(ix->n_raw);
     r.queries = d_queries;
     r.nq = static_cast<uint32_t>(nq);
     r.dim = ix->dim;

@@ -408,7 +408,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
       float d = row_distance<AB_QUANT_NONE, IP, TPV, MAXC>(reinterpret_cast<const uint8_t *>(a.raw) + size_t(cv) * a.raw_stride,
                                                           a.nchunks, lg, qs, act);
       if (act && lg == 0) {
-        if (a.valid != nullptr && ((a.valid[cv >> 5] >> (cv & 31)) & 1u) == 0) d = FLT_MAX;
+        // RawSpace::QueryComputer checks the raw storage's validity bit (raw_space.hpp:297-300): rows the
+        // raw space never received (SQ inserts, graph_update_job.hpp:75) and tombstones score FLT_MAX
+        if (cv >= a.n_rows || (a.valid != nullptr && ((a.valid[cv >> 5] >> (cv & 31)) & 1u) == 0)) d = FLT_MAX;
         ld[k] = d;
       }
     }

@@ -49,6 +49,7 @@ struct RerankArgs {
   size_t raw_stride; // bytes
   int nchunks;
   const uint32_t *valid;
+  uint32_t n_rows;  // rows the raw space holds; ids past it score FLT_MAX (not valid in the raw storage)
   const float *queries;
   uint32_t nq, dim, ef, topk;
   int metric;
