@@ -167,6 +167,114 @@ __device__ __forceinline__ float row_distance(const uint8_t *row, int nchunks, i
   return IP ? -acc : acc;
 }
 
+// ---- raw-space fast path --------------------------------------------------------------------------
+// The query slice of a lane lives in registers (CPL chunks per lane, lane l of a TPV-wide group owns
+// chunks l, l+TPV, ...), row chunks arrive as two packed-f32x2 halves per 128-bit load, and the
+// arithmetic uses Blackwell's packed fp32 pipe (sub.f32x2 / fma.rn.f32x2 -> FADD2 / FFMA2): 4 FP
+// instructions per 16-byte chunk instead of 8. Two candidates per group are in flight at once, so a
+// lane has up to 2*CPL independent 128-bit loads outstanding before the first FMA.
+struct U64x2 {
+  unsigned long long a, b;
+};
+__device__ __forceinline__ U64x2 ldg128_pairs(const void *p) {
+  U64x2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2sub(unsigned long long x, unsigned long long y) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  return d;
+}
+__device__ __forceinline__ unsigned long long f2fma(unsigned long long x, unsigned long long y, unsigned long long z) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z));
+  return d;
+}
+__device__ __forceinline__ float f2sum(unsigned long long x) {
+  return __uint_as_float(static_cast<uint32_t>(x)) + __uint_as_float(static_cast<uint32_t>(x >> 32));
+}
+
+template <bool IP>
+__device__ __forceinline__ unsigned long long raw_pairs_term(const U64x2 &q, const U64x2 &x, unsigned long long acc) {
+  if (IP) {
+    acc = f2fma(q.a, x.a, acc);
+    acc = f2fma(q.b, x.b, acc);
+  } else {
+    const unsigned long long d0 = f2sub(q.a, x.a), d1 = f2sub(q.b, x.b);
+    acc = f2fma(d0, d0, acc);
+    acc = f2fma(d1, d1, acc);
+  }
+  return acc;
+}
+
+// load this lane's query slice from the staged (zero padded) query in shared memory
+template <int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ void load_query_regs(const float *q_smem, int nchunks, int lg, U64x2 (&q)[CPL]) {
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    const int ch = lg + i * TPV;
+    if (EXACT || ch < nchunks) {
+      const ulonglong2 t = reinterpret_cast<const ulonglong2 *>(q_smem)[ch];
+      q[i].a = t.x;
+      q[i].b = t.y;
+    } else {
+      q[i].a = 0ull;
+      q[i].b = 0ull;
+    }
+  }
+}
+
+// rows r0 / r1 already point at this lane's first chunk (row + lg * 16)
+template <bool IP, int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ void raw_distance2(const uint8_t *r0, const uint8_t *r1, const U64x2 (&q)[CPL], int nchunks, int lg,
+                                              float &d0, float &d1) {
+  U64x2 x0[CPL], x1[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    if (EXACT || lg + i * TPV < nchunks) {
+      x0[i] = ldg128_pairs(r0 + i * TPV * 16);
+      x1[i] = ldg128_pairs(r1 + i * TPV * 16);
+    } else {
+      x0[i].a = x0[i].b = x1[i].a = x1[i].b = 0ull;
+    }
+  }
+  unsigned long long a0 = 0ull, a1 = 0ull;
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    a0 = raw_pairs_term<IP>(q[i], x0[i], a0);
+    a1 = raw_pairs_term<IP>(q[i], x1[i], a1);
+  }
+  float s0 = f2sum(a0), s1 = f2sum(a1);
+#pragma unroll
+  for (int o = TPV / 2; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
+    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+  }
+  d0 = IP ? -s0 : s0;
+  d1 = IP ? -s1 : s1;
+}
+
+template <bool IP, int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ float raw_distance1(const uint8_t *r0, const U64x2 (&q)[CPL], int nchunks, int lg) {
+  U64x2 x0[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    if (EXACT || lg + i * TPV < nchunks) {
+      x0[i] = ldg128_pairs(r0 + i * TPV * 16);
+    } else {
+      x0[i].a = x0[i].b = 0ull;
+    }
+  }
+  unsigned long long a0 = 0ull;
+#pragma unroll
+  for (int i = 0; i < CPL; i++) a0 = raw_pairs_term<IP>(q[i], x0[i], a0);
+  float s0 = f2sum(a0);
+#pragma unroll
+  for (int o = TPV / 2; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
+  return IP ? -s0 : s0;
+}
+
 // ---- quantizer (include/space/quant/sq8.hpp:120-132, sq4.hpp:120-132) --------------------------
 // IEEE round-to-nearest sub / div / mul with no contraction, then truncation, so that codes equal
 // the host's static_cast<uint8_t>(((float)v - min) / (max - min) * levels).

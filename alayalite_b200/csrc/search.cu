@@ -113,6 +113,7 @@ __device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, 
 }
 
 // Evaluate the search-space distance of the candidate held by every lane with want == true.
+// Generic path: query in shared memory, any space (distance.cuh row_distance).
 template <int QUANT, bool IP, int TPV, int MAXC>
 __device__ __forceinline__ float eval_lanes(const SearchArgs &a, const WarpSmem &ws, const QuerySmem &qs,
                                             uint32_t v, bool want, int lane) {
@@ -140,8 +141,54 @@ __device__ __forceinline__ float eval_lanes(const SearchArgs &a, const WarpSmem 
   return out;
 }
 
-template <int QUANT, bool IP, int TPV, int MAXC>
+// Raw-space fast path: query slice in registers, packed fp32 math, two candidates per group in
+// flight (distance.cuh raw_distance2).
+template <bool IP, int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpSmem &ws, const U64x2 (&q)[CPL], uint32_t v,
+                                                bool want, int lane) {
+  constexpr int G = 32 / TPV;
+  const uint32_t mask = __ballot_sync(kFull, want);
+  const int cnt = __popc(mask);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  if (want) ws.cand[rank] = v;
+  __syncwarp();
+  const int g = lane / TPV, lg = lane % TPV;
+  const uint8_t *lane_base = a.rows + lg * 16;
+  for (int base = 0; base < cnt; base += 2 * G) {
+    const int k0 = base + g, k1 = k0 + G;
+    const bool act0 = k0 < cnt, act1 = k1 < cnt;
+    const uint32_t c0 = ws.cand[act0 ? k0 : 0];
+    float d0, d1 = 0.f;
+    uint32_t c1 = c0;
+    if (cnt - base > G) {  // warp-uniform: a second candidate exists for at least one group
+      c1 = ws.cand[act1 ? k1 : 0];
+      raw_distance2<IP, TPV, CPL, EXACT>(lane_base + size_t(c0) * a.row_stride, lane_base + size_t(c1) * a.row_stride, q,
+                                         a.nchunks, lg, d0, d1);
+    } else {
+      d0 = raw_distance1<IP, TPV, CPL, EXACT>(lane_base + size_t(c0) * a.row_stride, q, a.nchunks, lg);
+    }
+    if (lg == 0) {
+      if (a.valid != nullptr) {  // RawSpace::QueryComputer: FLT_MAX for tombstoned rows (raw_space.hpp:297-304)
+        if (((a.valid[c0 >> 5] >> (c0 & 31)) & 1u) == 0) d0 = FLT_MAX;
+        if (((a.valid[c1 >> 5] >> (c1 & 31)) & 1u) == 0) d1 = FLT_MAX;
+      }
+      if (act0) ws.cdist[k0] = d0;
+      if (act1) ws.cdist[k1] = d1;
+    }
+  }
+  __syncwarp();
+  const float out = want ? ws.cdist[rank] : FLT_MAX;
+  __syncwarp();
+  return out;
+}
+
+// CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
+// CPL == 0 is the generic path for any space.
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
 __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
+  constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
+  constexpr int MAXC = 8;
+  constexpr int QREGS = FAST ? CPL : 1;
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
@@ -242,7 +289,10 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
 
     // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
     uint32_t u = a.ep;
-    float cur_d = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, u, lane == 0, lane);
+    U64x2 qreg[QREGS];
+    if (FAST) load_query_regs<TPV, QREGS, EXACT>(ws.q_raw, a.nchunks, lane % TPV, qreg);
+#define AB_EVAL(ID, WANT) (FAST ? eval_lanes_raw<IP, TPV, QREGS, EXACT>(a, ws, qreg, ID, WANT, lane) : eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, ID, WANT, lane))
+    float cur_d = AB_EVAL(u, lane == 0);
     cur_d = __shfl_sync(kFull, cur_d, 0);
     ndc_ov += 1;
     if (a.ov_off != nullptr) {
@@ -255,7 +305,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
           const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
           const int cnt = empties ? __ffs(empties) - 1 : kR;
           const bool want = lane < cnt;
-          float d = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, v, want, lane);
+          float d = AB_EVAL(v, want);
           ndc_ov += cnt;
           // sequential "if (dist < cur_dist)" scan == first index attaining the minimum, if < cur_d
           float best = want ? d : FLT_MAX;
@@ -302,6 +352,11 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
         cur = nxt;
       }
       hops++;
+      // the closest un-expanded entry is the likely next hop: pull its adjacency row towards L2 now
+      if (lane == 0 && cur < size) {
+        const uint32_t nx = ws.pool_i[cur] & kIdMask;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
+      }
 
       const uint32_t v = a.adj[size_t(u) * kR + lane];
       const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
@@ -313,7 +368,7 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
       if (nnew == 0) continue;
       nvis += nnew;
       ndc += nnew;
-      const float d = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, v, is_new, lane);
+      const float d = AB_EVAL(v, is_new);
 
       // inserts in neighbour order. A candidate that fails "d < worst" against a full pool now can
       // only fail later too (worst never grows), so pre-filtering is exact.
@@ -356,6 +411,8 @@ __global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
     __syncwarp();
   }
 }
+
+#undef AB_EVAL
 
 // PyIndex::rerank (python/include/index.hpp:450-467): exact raw-space distance for the ef entries of
 // res_pool -- the topk ids search wrote plus (ef - topk) untouched zeros -- ordered by (dist, id).
@@ -444,22 +501,49 @@ int pick_tpv(int nchunks) {
   return 4;
 }
 
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
+void launch_one(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
+  auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT>;
+  AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes)));
+  kern<<<dim3(p.ctas), dim3(p.warps_per_cta * 32), p.smem_bytes, s>>>(a);
+}
+
+// raw space: register-resident query, TPV * CPL chunks per row
+template <bool IP>
+bool launch_raw_fast(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
+  const int n = a.nchunks;
+#define AB_FAST(T, C)                                                   \
+  if (n == T * C) { launch_one<AB_QUANT_NONE, IP, T, C, true>(p, a, s); return true; }
+#define AB_FAST_LE(T, C)                                                \
+  if (n <= T * C) { launch_one<AB_QUANT_NONE, IP, T, C, false>(p, a, s); return true; }
+  AB_FAST(8, 3)    // d = 96
+  AB_FAST(8, 4)    // d = 128
+  AB_FAST(16, 4)   // d = 256
+  AB_FAST(32, 4)   // d = 512
+  AB_FAST(32, 6)   // d = 768
+  AB_FAST_LE(8, 2)
+  AB_FAST_LE(8, 4)
+  AB_FAST_LE(16, 4)
+  AB_FAST_LE(32, 4)
+  AB_FAST_LE(32, 8)  // up to d = 1024 (d = 960 lands here)
+#undef AB_FAST
+#undef AB_FAST_LE
+  return false;
+}
+
 template <int QUANT, bool IP>
 void launch_search_t(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
-  const dim3 grid(p.ctas), block(p.warps_per_cta * 32);
-#define AB_LAUNCH(TPV)                                                                                          \
-  {                                                                                                             \
-    auto kern = beam_search_kernel<QUANT, IP, TPV, 8>;                                                          \
-    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes))); \
-    kern<<<grid, block, p.smem_bytes, s>>>(a);                                                                  \
+  if (QUANT == AB_QUANT_NONE && launch_raw_fast<IP>(p, a, s)) {
+    AB_CUDA(cudaGetLastError());
+    count_launch();
+    return;
   }
   switch (p.tpv) {
-    case 4: AB_LAUNCH(4); break;
-    case 8: AB_LAUNCH(8); break;
-    case 16: AB_LAUNCH(16); break;
-    default: AB_LAUNCH(32); break;
+    case 4: launch_one<QUANT, IP, 4, 0, false>(p, a, s); break;
+    case 8: launch_one<QUANT, IP, 8, 0, false>(p, a, s); break;
+    case 16: launch_one<QUANT, IP, 16, 0, false>(p, a, s); break;
+    default: launch_one<QUANT, IP, 32, 0, false>(p, a, s); break;
   }
-#undef AB_LAUNCH
   AB_CUDA(cudaGetLastError());
   count_launch();
 }
