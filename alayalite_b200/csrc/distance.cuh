@@ -172,7 +172,9 @@ __device__ __forceinline__ float row_distance(const uint8_t *row, int nchunks, i
 // chunks l, l+TPV, ...), row chunks arrive as two packed-f32x2 halves per 128-bit load, and the
 // arithmetic uses Blackwell's packed fp32 pipe (sub.f32x2 / fma.rn.f32x2 -> FADD2 / FFMA2): 4 FP
 // instructions per 16-byte chunk instead of 8. Two candidates per group are in flight at once, so a
-// lane has up to 2*CPL independent 128-bit loads outstanding before the first FMA.
+// lane has up to 2*CPL independent 128-bit loads outstanding before the first FMA. The loads and the
+// packed arithmetic are volatile asm on purpose: ptxas otherwise sinks the loads next to their uses
+// to save registers, which serialises the round trips (seen in the r01 SASS: 2 loads in flight, not 8).
 struct U64x2 {
   unsigned long long a, b;
 };
@@ -183,12 +185,12 @@ __device__ __forceinline__ U64x2 ldg128_pairs(const void *p) {
 }
 __device__ __forceinline__ unsigned long long f2sub(unsigned long long x, unsigned long long y) {
   unsigned long long d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
   return d;
 }
 __device__ __forceinline__ unsigned long long f2fma(unsigned long long x, unsigned long long y, unsigned long long z) {
   unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z));
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z));
   return d;
 }
 __device__ __forceinline__ float f2sum(unsigned long long x) {

@@ -185,7 +185,7 @@ __device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpS
 // CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
 // CPL == 0 is the generic path for any space.
 template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
-__global__ void __launch_bounds__(256) beam_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? 3 : 1) beam_search_kernel(const SearchArgs a) {
   constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
   constexpr int MAXC = 8;
   constexpr int QREGS = FAST ? CPL : 1;
