@@ -62,7 +62,7 @@ def load_traffic():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f)
+            return json.load(f).get("total")
     return None
 
 
