@@ -21,23 +21,31 @@ CONFIGS = {
 }
 
 
-def low_rank(n: int, dim: int, nq: int, latent: int = 16, seed: int = 42, noise: float = 0.05, normalize: bool = False, chunk: int = 1 << 18):
-    """Base [n, dim] and queries [nq, dim], float32, from one seeded stream (A, then base, then queries)."""
+def low_rank(n: int, dim: int, nq: int, latent: int = 16, seed: int = 42, noise: float = 0.05, normalize: bool = False, chunk: int = 1 << 18,
+             shard: int = 0):
+    """Base [n, dim] and queries [nq, dim], float32, from one seeded stream (A, then base, then queries).
+    shard > 0 draws another n rows of the SAME distribution (same mixing matrix A) from an independent
+    stream: the rows of shard `shard` of a larger sharded index. Queries always come from the seed's
+    own stream, so every shard sees the same queries."""
     rng = np.random.default_rng(seed)
     a = (rng.standard_normal((latent, dim)) / np.sqrt(latent)).astype(np.float32)
 
-    def gen(m):
+    def gen(m, r):
         out = np.empty((m, dim), np.float32)
         for s in range(0, m, chunk):
             e = min(m, s + chunk)
-            z = rng.standard_normal((e - s, latent), dtype=np.float32)
+            z = r.standard_normal((e - s, latent), dtype=np.float32)
             out[s:e] = z @ a
-            out[s:e] += noise * rng.standard_normal((e - s, dim), dtype=np.float32)
+            out[s:e] += noise * r.standard_normal((e - s, dim), dtype=np.float32)
         if normalize:
             out /= np.linalg.norm(out, axis=1, keepdims=True)
         return out
 
-    return gen(n), gen(nq)
+    if shard == 0:
+        return gen(n, rng), gen(nq, rng)
+    base = gen(n, np.random.default_rng([seed, shard]))
+    gen(n, rng)  # advance the seed's stream past shard 0's rows so the queries are the shared ones
+    return base, gen(nq, rng)
 
 
 def uniform(n: int, dim: int, nq: int, seed: int = 0):

@@ -225,12 +225,8 @@ def ours_arm(args, rank, world, local_rank):
 
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- data: every rank owns one shard (seed 42 + rank); queries are shared ---------------------
-    base, _ = low_rank(N_BASE, DIM, 1, LATENT, seed=42 + rank)
-    if rank == 0:
-        _, q = low_rank(N_BASE, DIM, NQ, LATENT, seed=42)
-    else:
-        q = np.empty((NQ, DIM), np.float32)
+    # ---- data: every rank owns one shard (same generator, independent stream per rank); queries are shared ---------------------
+    base, q = low_rank(N_BASE, DIM, NQ, LATENT, seed=42, shard=rank)  # same distribution and queries on every rank
     qt = torch.from_numpy(q).pin_memory()
     d_q = qt.to(dev)
     if world > 1:
