@@ -23,7 +23,6 @@
 // Distances are plain fp32; given equal distance values the traversal is step-for-step the
 // reference's, so ids are identical up to fp32 summation-order effects.
 #include <cfloat>
-#include <type_traits>
 
 #include "distance.cuh"
 #include "search.cuh"
@@ -113,157 +112,6 @@ __device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, 
   if (pos < cur) cur = pos;
 }
 
-// ---- the candidate pool, two homes ---------------------------------------------------------------
-// Both implement LinearPool (query_utils.hpp:237-312) exactly: sorted ascending, capacity ef, upper-bound
-// insert position, "expanded" flag in bit 31 of the id, cursor = first un-expanded entry.
-// All members are warp-collective with warp-uniform arguments.
-
-// (a) shared memory, any ef
-struct SmemPool {
-  float *pd;
-  uint32_t *pi;
-  int size, cur, ef;
-  __device__ __forceinline__ void init(const WarpSmem &ws, int ef_, int lane) {
-    pd = ws.pool_d;
-    pi = ws.pool_i;
-    ef = ef_;
-    size = cur = 0;
-    for (int i = lane; i <= ef; i += 32) {
-      pd[i] = 0.f;
-      pi[i] = 0u;
-    }
-    __syncwarp();
-  }
-  __device__ __forceinline__ bool has_next() const { return cur < size; }
-  __device__ __forceinline__ bool full() const { return size == ef; }
-  __device__ __forceinline__ float worst() const { return pd[size - 1]; }
-  __device__ __forceinline__ void insert(float d, uint32_t v, int lane) { pool_insert(pd, pi, size, cur, ef, d, v, lane); }
-  __device__ __forceinline__ uint32_t pop(int lane) {  // LinearPool::pop (query_utils.hpp:284-293)
-    const uint32_t u = pi[cur];
-    __syncwarp();
-    if (lane == 0) pi[cur] = u | kCheckedBit;
-    __syncwarp();
-    int nxt = size;
-    for (int base = cur + 1; base < size; base += 32) {
-      const int i = base + lane;
-      const uint32_t b = __ballot_sync(kFull, i < size && (pi[i] & kCheckedBit) == 0);
-      if (b) {
-        nxt = base + __ffs(b) - 1;
-        break;
-      }
-    }
-    cur = nxt;
-    return u;
-  }
-  __device__ __forceinline__ uint32_t next_id() const { return pi[cur] & kIdMask; }
-  // entry i for the lanes' own i (any i <= ef; zero past size)
-  __device__ __forceinline__ void get(int i, uint32_t &id, float &d) const {
-    id = pi[i] & kIdMask;
-    d = pd[i];
-  }
-};
-
-// (b) registers, ef <= 32 * S: entry i lives in lane i % 32, slot i / 32. Insert = two ballots for the
-// position and one shuffle-up per slot and field for the shift: no shared memory, no __syncwarp.
-template <int S>
-struct RegPool {
-  float d[S];
-  uint32_t id[S];
-  int size, cur, ef;
-  float worst_;
-  __device__ __forceinline__ void init(const WarpSmem &, int ef_, int) {
-    ef = ef_;
-    size = cur = 0;
-    worst_ = FLT_MAX;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      d[s] = 0.f;
-      id[s] = 0u;
-    }
-  }
-  __device__ __forceinline__ bool has_next() const { return cur < size; }
-  __device__ __forceinline__ bool full() const { return size == ef; }
-  __device__ __forceinline__ float worst() const { return worst_; }
-  __device__ __forceinline__ void insert(float nd, uint32_t nv, int lane) {
-    int pos = 0;
-#pragma unroll
-    for (int s = 0; s < S; s++) pos += __popc(__ballot_sync(kFull, s * 32 + lane < size && d[s] <= nd));
-    const int nsize = min(size + 1, ef);
-    float pd_[S];
-    uint32_t pi_[S];
-#pragma unroll
-    for (int s = 0; s < S; s++) {  // value of entry (index - 1), from the old contents
-      pd_[s] = __shfl_up_sync(kFull, d[s], 1);
-      pi_[s] = __shfl_up_sync(kFull, id[s], 1);
-      if (s > 0) {
-        const float cd = __shfl_sync(kFull, d[s - 1], 31);
-        const uint32_t ci = __shfl_sync(kFull, id[s - 1], 31);
-        if (lane == 0) {
-          pd_[s] = cd;
-          pi_[s] = ci;
-        }
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const int idx = s * 32 + lane;
-      if (idx == pos) {
-        d[s] = nd;
-        id[s] = nv;
-      } else if (idx > pos && idx < nsize) {
-        d[s] = pd_[s];
-        id[s] = pi_[s];
-      }
-    }
-    size = nsize;
-    if (pos < cur) cur = pos;
-    if (size == ef) {
-      float w = 0.f;
-#pragma unroll
-      for (int s = 0; s < S; s++) {
-        const float t = __shfl_sync(kFull, d[s], (ef - 1) & 31);
-        if (s == (ef - 1) >> 5) w = t;
-      }
-      worst_ = w;
-    }
-  }
-  __device__ __forceinline__ uint32_t pick_id(int i) const {
-    uint32_t r = 0;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const uint32_t t = __shfl_sync(kFull, id[s], i & 31);
-      if (s == i >> 5) r = t;
-    }
-    return r;
-  }
-  __device__ __forceinline__ uint32_t pop(int lane) {
-    const uint32_t u = pick_id(cur);
-#pragma unroll
-    for (int s = 0; s < S; s++)
-      if (s == cur >> 5 && lane == (cur & 31)) id[s] |= kCheckedBit;
-    int nxt = size;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const int idx = s * 32 + lane;
-      const uint32_t b = __ballot_sync(kFull, idx > cur && idx < size && (id[s] & kCheckedBit) == 0);
-      if (b && nxt == size) nxt = s * 32 + __ffs(b) - 1;
-    }
-    cur = nxt;
-    return u;
-  }
-  __device__ __forceinline__ uint32_t next_id() const { return pick_id(cur) & kIdMask; }
-  __device__ __forceinline__ void get(int i, uint32_t &oid, float &od) const {  // i = s * 32 + lane pattern only
-    oid = 0;
-    od = 0.f;
-#pragma unroll
-    for (int s = 0; s < S; s++)
-      if (s == i >> 5) {
-        oid = id[s] & kIdMask;
-        od = d[s];
-      }
-  }
-};
-
 // Evaluate the search-space distance of the candidate held by every lane with want == true.
 // Generic path: query in shared memory, any space (distance.cuh row_distance).
 template <int QUANT, bool IP, int TPV, int MAXC>
@@ -336,11 +184,9 @@ __device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpS
 
 // CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
 // CPL == 0 is the generic path for any space.
-// POOLS > 0 keeps the candidate pool in registers (ef <= 32 * POOLS), 0 in shared memory.
-template <int QUANT, bool IP, int TPV, int CPL, bool EXACT, int POOLS>
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
 __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? 3 : 1) beam_search_kernel(const SearchArgs a) {
   constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
-  using Pool = typename std::conditional<(POOLS > 0), RegPool<(POOLS > 0 ? POOLS : 1)>, SmemPool>::type;
   constexpr int MAXC = 8;
   constexpr int QREGS = FAST ? CPL : 1;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -430,10 +276,13 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       }
     }
     for (uint32_t i = lane; i < a.hash_size; i += 32) ws.hash[i] = kEmptyId;
-    Pool pool;
-    pool.init(ws, ef, lane);
+    for (int i = lane; i <= ef; i += 32) {
+      ws.pool_d[i] = 0.f;
+      ws.pool_i[i] = 0u;
+    }
     __syncwarp();
 
+    int size = 0, cur = 0;
     uint32_t nvis = 0;
     unsigned long long ndc = 0, hops = 0, ndc_ov = 0;
     vs.spilled = false;
@@ -478,19 +327,35 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         }
       }
     }
-    pool.insert(cur_d, u, lane);
+    pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, cur_d, u, lane);
     if (lane == 0) visit(vs, u);
     nvis = 1;
     __syncwarp();
 
     // ---- best-first search on level 0 (graph_search_job.hpp:307-331) ---------------------------
-    while (pool.has_next()) {
-      u = pool.pop(lane) & kIdMask;
+    while (cur < size) {
+      // LinearPool::pop (query_utils.hpp:284-293)
+      u = ws.pool_i[cur];
+      __syncwarp();
+      if (lane == 0) ws.pool_i[cur] = u | kCheckedBit;
+      __syncwarp();
+      {
+        int nxt = size;
+        for (int base = cur + 1; base < size; base += 32) {
+          const int i = base + lane;
+          const uint32_t b = __ballot_sync(kFull, i < size && (ws.pool_i[i] & kCheckedBit) == 0);
+          if (b) {
+            nxt = base + __ffs(b) - 1;
+            break;
+          }
+        }
+        cur = nxt;
+      }
       hops++;
       // the closest un-expanded entry is the likely next hop: pull its adjacency row towards L2 now
-      if (pool.has_next()) {
-        const uint32_t nx = pool.next_id();
-        if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
+      if (lane == 0 && cur < size) {
+        const uint32_t nx = ws.pool_i[cur] & kIdMask;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
       }
 
       const uint32_t v = a.adj[size_t(u) * kR + lane];
@@ -507,37 +372,30 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
 
       // inserts in neighbour order. A candidate that fails "d < worst" against a full pool now can
       // only fail later too (worst never grows), so pre-filtering is exact.
-      const float worst = pool.full() ? pool.worst() : FLT_MAX;
-      uint32_t acc = __ballot_sync(kFull, is_new && (!pool.full() || d < worst));
+      const float worst = size == ef ? ws.pool_d[size - 1] : FLT_MAX;
+      uint32_t acc = __ballot_sync(kFull, is_new && (size < ef || d < worst));
       while (acc) {
         const int j = __ffs(acc) - 1;
         acc &= acc - 1;
         const float dj = __shfl_sync(kFull, d, j);
         const uint32_t vj = __shfl_sync(kFull, v, j);
-        if (pool.full() && dj >= pool.worst()) continue;
-        pool.insert(dj, vj, lane);
+        if (size == ef && dj >= ws.pool_d[size - 1]) continue;
+        pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, dj, vj, lane);
       }
     }
 
     // ---- results ----------------------------------------------------------------------------
-    // slots past the pool size are zero, like the reference's zero-initialised pool
     for (uint32_t i = lane; i < a.topk; i += 32) {
-      uint32_t rid;
-      float rd;
-      pool.get(static_cast<int>(i), rid, rd);
-      const bool in = static_cast<int>(i) < pool.size;
-      a.out_ids[size_t(qi) * a.topk + i] = in ? rid : 0u;
-      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = in ? rd : 0.f;
+      const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
+      a.out_ids[size_t(qi) * a.topk + i] = in ? (ws.pool_i[i] & kIdMask) : 0u;
+      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = in ? ws.pool_d[i] : 0.f;
     }
     if (a.pool_ids) {
       for (int i = lane; i < ef; i += 32) {
-        uint32_t rid;
-        float rd;
-        pool.get(i, rid, rd);
-        a.pool_ids[size_t(qi) * a.ef + i] = i < pool.size ? rid : 0u;
-        a.pool_dist[size_t(qi) * a.ef + i] = i < pool.size ? rd : 0.f;
+        a.pool_ids[size_t(qi) * a.ef + i] = i < size ? (ws.pool_i[i] & kIdMask) : 0u;
+        a.pool_dist[size_t(qi) * a.ef + i] = i < size ? ws.pool_d[i] : 0.f;
       }
-      if (lane == 0) a.pool_sizes[qi] = pool.size;
+      if (lane == 0) a.pool_sizes[qi] = size;
     }
     if (vs.spilled) {
       // give the private bitmap back all-zero (the reference allocates + zeroes one per query)
@@ -643,34 +501,34 @@ int pick_tpv(int nchunks) {
   return 4;
 }
 
-template <int QUANT, bool IP, int TPV, int CPL, bool EXACT, int POOLS>
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
 void launch_one(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
-  auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT, POOLS>;
+  auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT>;
   AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes)));
   kern<<<dim3(p.ctas), dim3(p.warps_per_cta * 32), p.smem_bytes, s>>>(a);
 }
 
-// raw space: register-resident query slice (TPV * CPL chunks per row) and, for ef <= 128, a
-// register-resident pool
-template <bool IP, int TPV, int CPL, bool EXACT>
-void launch_raw_pool(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
-  if (a.ef <= 32) launch_one<AB_QUANT_NONE, IP, TPV, CPL, EXACT, 1>(p, a, s);
-  else if (a.ef <= 64) launch_one<AB_QUANT_NONE, IP, TPV, CPL, EXACT, 2>(p, a, s);
-  else if (a.ef <= 128) launch_one<AB_QUANT_NONE, IP, TPV, CPL, EXACT, 4>(p, a, s);
-  else launch_one<AB_QUANT_NONE, IP, TPV, CPL, EXACT, 0>(p, a, s);
-}
-
+// raw space: register-resident query, TPV * CPL chunks per row
 template <bool IP>
 bool launch_raw_fast(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
   const int n = a.nchunks;
-  if (n == 8 * 3) launch_raw_pool<IP, 8, 3, true>(p, a, s);         // d = 96
-  else if (n == 8 * 4) launch_raw_pool<IP, 8, 4, true>(p, a, s);    // d = 128
-  else if (n == 32 * 6) launch_raw_pool<IP, 32, 6, true>(p, a, s);  // d = 768
-  else if (n <= 8 * 4) launch_raw_pool<IP, 8, 4, false>(p, a, s);
-  else if (n <= 32 * 4) launch_raw_pool<IP, 32, 4, false>(p, a, s);
-  else if (n <= 32 * 8) launch_raw_pool<IP, 32, 8, false>(p, a, s);  // up to d = 1024 (d = 960 lands here)
-  else return false;
-  return true;
+#define AB_FAST(T, C)                                                   \
+  if (n == T * C) { launch_one<AB_QUANT_NONE, IP, T, C, true>(p, a, s); return true; }
+#define AB_FAST_LE(T, C)                                                \
+  if (n <= T * C) { launch_one<AB_QUANT_NONE, IP, T, C, false>(p, a, s); return true; }
+  AB_FAST(8, 3)    // d = 96
+  AB_FAST(8, 4)    // d = 128
+  AB_FAST(16, 4)   // d = 256
+  AB_FAST(32, 4)   // d = 512
+  AB_FAST(32, 6)   // d = 768
+  AB_FAST_LE(8, 2)
+  AB_FAST_LE(8, 4)
+  AB_FAST_LE(16, 4)
+  AB_FAST_LE(32, 4)
+  AB_FAST_LE(32, 8)  // up to d = 1024 (d = 960 lands here)
+#undef AB_FAST
+#undef AB_FAST_LE
+  return false;
 }
 
 template <int QUANT, bool IP>
@@ -681,10 +539,10 @@ void launch_search_t(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
     return;
   }
   switch (p.tpv) {
-    case 4: launch_one<QUANT, IP, 4, 0, false, 0>(p, a, s); break;
-    case 8: launch_one<QUANT, IP, 8, 0, false, 0>(p, a, s); break;
-    case 16: launch_one<QUANT, IP, 16, 0, false, 0>(p, a, s); break;
-    default: launch_one<QUANT, IP, 32, 0, false, 0>(p, a, s); break;
+    case 4: launch_one<QUANT, IP, 4, 0, false>(p, a, s); break;
+    case 8: launch_one<QUANT, IP, 8, 0, false>(p, a, s); break;
+    case 16: launch_one<QUANT, IP, 16, 0, false>(p, a, s); break;
+    default: launch_one<QUANT, IP, 32, 0, false>(p, a, s); break;
   }
   AB_CUDA(cudaGetLastError());
   count_launch();
