@@ -612,7 +612,11 @@ static void bruteforce_device_impl(int32_t metric, const float *d_data, uint64_t
     rows = pr.p;
     qs = pq.p;
   }
-  bruteforce_topk(metric, rows, n, stride, qs, nq, stride, k, d_out_ids, d_out_dist, sms, s);
+  if (bruteforce_tc_applicable(n, nq, k) && n >= k) {
+    bruteforce_topk_tc(metric, rows, n, dim, stride, qs, nq, stride, k, d_out_ids, d_out_dist, sms, s);
+  } else {
+    bruteforce_topk(metric, rows, n, stride, qs, nq, stride, k, d_out_ids, d_out_dist, sms, s);
+  }
   AB_CUDA(cudaStreamSynchronize(s));
 }
 
