@@ -23,8 +23,9 @@
 //   warp 1      TMEM allocation + single-thread tcgen05.mma.cta_group::1.kind::tf32 issue,
 //               M = 128, N = 256, K = 8 per instruction; two 256-column accumulators (all 512 TMEM
 //               columns) so the epilogue of tile t overlaps the MMAs of tile t + 1
-//   warps 4-7   epilogue: tcgen05.ld 32x32b (thread = one query row), compare against the query's
-//               threshold, append survivors to its candidate list
+//   warps 4-11  epilogue: tcgen05.ld 32x32b (thread = one query row x half of the columns); the minimum
+//               score of 32 columns is tested against the query's threshold first, survivors (rare) are
+//               appended to the query's candidate list
 // mbarriers: full/empty per stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator (MMA <-> epilogue).
 #include <cuda.h>
 
@@ -45,11 +46,11 @@ constexpr int TC_M = 128;       // queries per CTA (UMMA M, one TMEM lane each)
 constexpr int TC_N = 256;       // rows per tile (UMMA N, TMEM columns of one accumulator)
 constexpr int TC_KB = 32;       // fp32 elements per k-block = 128 bytes = one swizzle row
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // warp 0 TMA, warp 1 MMA, warps 4-11 epilogue (two per TMEM lane quadrant)
 constexpr uint32_t A_BYTES = TC_M * TC_KB * 4;  // 16 KB
 constexpr uint32_t B_BYTES = TC_N * TC_KB * 4;  // 32 KB
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr size_t TC_SMEM = 1024 + size_t(TC_STAGES) * STAGE_BYTES + 2 * TC_N * 4 + 256;
+constexpr size_t TC_SMEM = 1024 + size_t(TC_STAGES) * STAGE_BYTES + 2 * TC_N * 4 + TC_M * 4 + 256;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -143,7 +144,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *stage_base = smem;  // [stages][A 16 KB | B 32 KB], every tile 1024-byte aligned
   float *sx = reinterpret_cast<float *>(smem + size_t(TC_STAGES) * STAGE_BYTES);  // [2][TC_N] row terms
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sx + 2 * TC_N);
+  uint32_t *scnt = reinterpret_cast<uint32_t *>(sx + 2 * TC_N);  // [TC_M] survivors per query row
+  uint64_t *bars = reinterpret_cast<uint64_t *>(scnt + TC_M);
   uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 2 * TC_STAGES + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
 
@@ -155,6 +157,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   const uint64_t tile_end = min(total_tiles, tile_begin + a.tiles_per_split);
   const uint32_t ntiles = tile_end > tile_begin ? static_cast<uint32_t>(tile_end - tile_begin) : 0u;
 
+  if (threadIdx.x < TC_M) scnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; s++) {
       mbar_init(&full[s], 1);
@@ -162,7 +165,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(&tfull[b], 1);
-      mbar_init(&tempty[b], 128);
+      mbar_init(&tempty[b], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,12 +218,12 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: thread e owns query row q0 + e =====
+    // ===== epilogue: 256 threads; thread e scans columns [half * 128, half * 128 + 128) of query row q0 + (e & 127) =====
     const uint32_t e = threadIdx.x - 128;
-    const uint32_t q = q0 + e;
+    const uint32_t row = e & 127u, half = e >> 7;
+    const uint32_t q = q0 + row;
     const bool qvalid = q < a.nq;
-    const float thr = qvalid ? a.thr[q] : -FLT_MAX;
-    uint32_t cnt = 0;
+    const float thr = qvalid ? a.thr[q] : -INFINITY;
     uint32_t *my = a.cand + (size_t(split) * a.nq + (qvalid ? q : 0)) * a.cap;
     const uint32_t lane_quadrant = (uint32_t(warp & 3) * 32u) << 16;
     for (uint32_t t = 0; t < ntiles; t++) {
@@ -229,27 +232,40 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       float *sxb = sx + b * TC_N;
       // per-row terms of this tile; rows past n can never pass the threshold
       sxb[e] = r0 + e < a.n ? a.xnorm[r0 + e] : INFINITY;
-      sxb[e + 128] = r0 + e + 128 < a.n ? a.xnorm[r0 + e + 128] : INFINITY;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull[b], (t >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (uint32_t c = 0; c < TC_N / 32; c++) {
+      for (uint32_t c = 0; c < TC_N / 64; c++) {
+        const uint32_t col = half * (TC_N / 2) + c * 32;
         uint32_t v[32];
-        tmem_ld32(tmem_base + lane_quadrant + b * TC_N + c * 32, v);
+        tmem_ld32(tmem_base + lane_quadrant + b * TC_N + col, v);
+        // cheap test first: the minimum approximate score of the 32 columns
+        float m = INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float s = fmaf(a.alpha, __uint_as_float(v[j]), sxb[c * 32 + j]);
-          if (s <= thr) {
-            if (cnt < a.cap) my[cnt] = static_cast<uint32_t>(r0 + c * 32 + j);
-            cnt++;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 s4 = *reinterpret_cast<const float4 *>(sxb + col + j);
+          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 0]), s4.x));
+          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 1]), s4.y));
+          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 2]), s4.z));
+          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 3]), s4.w));
+        }
+        if (m <= thr) {  // rare: some column survives
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float s = fmaf(a.alpha, __uint_as_float(v[j]), sxb[col + j]);
+            if (s <= thr) {
+              const uint32_t pos = atomicAdd(&scnt[row], 1u);
+              if (pos < a.cap) my[pos] = static_cast<uint32_t>(r0 + col + j);
+            }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[b]);
     }
-    if (qvalid) a.counts[size_t(split) * a.nq + q] = cnt;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (qvalid && half == 0) a.counts[size_t(split) * a.nq + q] = scnt[row];
   }
   tc_fence_before();
   __syncthreads();
@@ -310,39 +326,55 @@ __global__ void __launch_bounds__(128) refine_kernel(const float *__restrict__ r
                                                      uint32_t *__restrict__ redo_flags) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  const size_t per_warp = size_t(nchunks) * 16 + size_t(k) * 8 + 64 * 4;
+  const size_t per_warp = round_up16(size_t(nchunks) * 16 + size_t(k) * 8 + 64 * 4);
   uint8_t *wb = smem + size_t(warp) * per_warp;
   float *qs_raw = reinterpret_cast<float *>(wb);
   float *td = reinterpret_cast<float *>(wb + size_t(nchunks) * 16);
   uint32_t *ti = reinterpret_cast<uint32_t *>(td + k);
-  float *scratch = reinterpret_cast<float *>(ti + k);  // [32] distances of one pass
-  uint32_t *sids = reinterpret_cast<uint32_t *>(scratch + 32);
-  QuerySmem qs{qs_raw, nullptr, nullptr, nullptr};
   for (uint64_t q = uint64_t(blockIdx.x) * warps + warp; q < nq; q += uint64_t(gridDim.x) * warps) {
     for (int c = lane; c < nchunks; c += 32)
       reinterpret_cast<uint4 *>(qs_raw)[c] = reinterpret_cast<const uint4 *>(queries + q * qstride)[c];
     __syncwarp();
     int size = 0;
     bool overflow = false;
+    const int nfl = nchunks * 4;
     for (uint32_t sp = 0; sp < splits; sp++) {
       const uint32_t cnt = counts[size_t(sp) * nq + q];
       if (cnt > cap) overflow = true;
       const uint32_t m = min(cnt, cap);
       const uint32_t *lst = cand + (size_t(sp) * nq + q) * cap;
-      for (uint32_t base = 0; base < m; base += 8) {  // 8 rows per pass, 4 lanes per row
-        const uint32_t kk = base + (lane >> 2);
+      for (uint32_t base = 0; base < m; base += 32) {  // one survivor per lane
+        const uint32_t kk = base + lane;
         const bool act = kk < m;
         const uint32_t id = act ? lst[kk] : 0u;
-        const float d = row_distance<AB_QUANT_NONE, IP, 4, 8>(reinterpret_cast<const uint8_t *>(rows) + size_t(id) * stride * 4, nchunks,
-                                                             lane & 3, qs, act);
-        if ((lane & 3) == 0) {
-          scratch[lane >> 2] = d;
-          sids[lane >> 2] = id;
+        // same arithmetic as bf_tile_kernel: one accumulator, dimension order, FMA -> identical distances
+        const float4 *xr = reinterpret_cast<const float4 *>(rows + size_t(id) * stride);
+        float acc = 0.f;
+        if (act) {
+          for (int c = 0; c < nfl / 4; c++) {
+            const float4 x = xr[c];
+            const float4 qq = reinterpret_cast<const float4 *>(qs_raw)[c];
+            if (IP) {
+              acc = fmaf(qq.x, x.x, acc);
+              acc = fmaf(qq.y, x.y, acc);
+              acc = fmaf(qq.z, x.z, acc);
+              acc = fmaf(qq.w, x.w, acc);
+            } else {
+              float df = qq.x - x.x;
+              acc = fmaf(df, df, acc);
+              df = qq.y - x.y;
+              acc = fmaf(df, df, acc);
+              df = qq.z - x.z;
+              acc = fmaf(df, df, acc);
+              df = qq.w - x.w;
+              acc = fmaf(df, df, acc);
+            }
+          }
         }
-        __syncwarp();
-        const uint32_t valid = min(8u, m - base);
-        for (uint32_t j = 0; j < valid; j++) topk_insert(td, ti, size, static_cast<int>(k), scratch[j], sids[j], lane);
-        __syncwarp();
+        const float d = IP ? -acc : acc;
+        const uint32_t valid = min(32u, m - base);
+        for (uint32_t j = 0; j < valid; j++)
+          topk_insert(td, ti, size, static_cast<int>(k), __shfl_sync(0xFFFFFFFFu, d, j), __shfl_sync(0xFFFFFFFFu, id, j), lane);
       }
     }
     for (uint32_t i = lane; i < k; i += 32) {
@@ -413,7 +445,7 @@ void bruteforce_topk_tc(int metric, const float *d_rows, uint64_t n, uint32_t di
   const bool l2 = metric == AB_METRIC_L2;
   AB_CHECK(n >= k && k <= 256, AB_ERR_INVALID, "bruteforce_topk_tc: needs k <= min(n, 256)");
   // ---- pass A: exact top-k over a sample -> tau ---------------------------------------------------
-  const uint64_t sample = std::min<uint64_t>(n, std::max<uint64_t>(32768, n / 16));
+  const uint64_t sample = std::min<uint64_t>(n, std::max<uint64_t>(16384, n / 32));
   DevBuf<float> sd, xnorm, qnorm, thr, rd;
   DevBuf<uint32_t> si, maxbits, cand, counts, redo, ri;
   sd.reserve(nq * k);
@@ -467,7 +499,7 @@ void bruteforce_topk_tc(int metric, const float *d_rows, uint64_t n, uint32_t di
   const uint32_t need = static_cast<uint32_t>(std::min<uint64_t>(k, n));
   const int nchunks = static_cast<int>(stride / 4);
   const int warps = 4;
-  const size_t smem = (size_t(nchunks) * 16 + size_t(k) * 8 + 64 * 4) * warps;
+  const size_t smem = round_up16(size_t(nchunks) * 16 + size_t(k) * 8 + 64 * 4) * warps;
   const int blocks = static_cast<int>(std::min<uint64_t>((nq + warps - 1) / warps, uint64_t(sm_count) * 16));
   if (l2) {
     AB_CUDA(cudaFuncSetAttribute(refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -264,3 +264,41 @@ def test_bruteforce_gt_vs_float64(cabi, small_sets):
     want = np.argsort(d, axis=1, kind="stable")[:, :10]
     assert recall(gt, want) >= 0.999
     assert gt.dtype == np.int32
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 brute force: the TF32 GEMM is only a filter, the answer must equal the exact fp32 kernel
+@pytest.fixture
+def force_tc(monkeypatch):
+    def _set(on):
+        monkeypatch.setenv("AB_BRUTEFORCE_TC", "1" if on else "0")
+    return _set
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+@pytest.mark.parametrize("name,k", [("grid", 17), ("lowrank", 10), ("odd", 100), ("lowrank128", 10)])
+def test_bruteforce_tensor_core_path_is_exact(cabi, orc, small_sets, force_tc, metric, name, k):
+    base, q = small_sets[name]
+    force_tc(False)
+    ids0, d0 = cabi.bruteforce_topk(metric, base, q, k)
+    force_tc(True)
+    ids1, d1 = cabi.bruteforce_topk(metric, base, q, k)
+    assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1)  # same ids, bit-identical distances
+    if name == "grid":
+        oid, od = orc.bruteforce_topk(metric, q, base, k, threads=4)
+        assert np.array_equal(ids1, oid) and np.array_equal(d1, od)
+
+
+def test_bruteforce_tensor_core_large_and_ragged(cabi, force_tc):
+    """Sizes that are not multiples of the 128 x 256 tile, more rows than one split, adversarial order
+    (rows sorted by norm, so the leading sample is a poor predictor and survivor lists overflow)."""
+    from alayalite_b200.synthetic import low_rank
+
+    base, q = low_rank(70001, 100, 333, latent=12, seed=23)
+    order = np.argsort((base ** 2).sum(1))[::-1]
+    base = np.ascontiguousarray(base[order])
+    force_tc(False)
+    ids0, d0 = cabi.bruteforce_topk("l2", base, q, 10)
+    force_tc(True)
+    ids1, d1 = cabi.bruteforce_topk("l2", base, q, 10)
+    assert np.array_equal(ids0, ids1) and np.array_equal(d0, d1)
