@@ -126,6 +126,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+
 struct TcArgs {
   uint64_t n, nq;
   uint32_t kblocks;        // ceil(dim / 32)
@@ -138,16 +150,24 @@ struct TcArgs {
   uint32_t cap;
 };
 
+// RESIDENT: the whole 128-query tile (kblocks <= 4, i.e. d <= 128) is loaded once and stays in shared memory;
+// only row tiles stream through the ring (2/3 of the L2 -> SM traffic per MMA). Otherwise both operands stream.
+template <bool RESIDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *stage_base = smem;  // [stages][A 16 KB | B 32 KB], every tile 1024-byte aligned
+  // streaming: [stages][A 16 KB | B 32 KB]; resident: [4 x A 16 KB][stages][B 32 KB]. Every tile 1024-byte aligned.
+  constexpr uint32_t kStage = RESIDENT ? B_BYTES : STAGE_BYTES;
+  constexpr uint32_t kBOff = RESIDENT ? 0u : A_BYTES;
+  uint8_t *res_a = smem;
+  uint8_t *stage_base = smem + (RESIDENT ? 4 * A_BYTES : 0);
   float *sx = reinterpret_cast<float *>(smem + size_t(TC_STAGES) * STAGE_BYTES);  // [2][TC_N] row terms
   uint32_t *scnt = reinterpret_cast<uint32_t *>(sx + 2 * TC_N);  // [TC_M] survivors per query row
   uint64_t *bars = reinterpret_cast<uint64_t *>(scnt + TC_M);
   uint64_t *full = bars, *empty = bars + TC_STAGES, *tfull = bars + 2 * TC_STAGES, *tempty = bars + 2 * TC_STAGES + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 4);
+  uint64_t *abar = bars + 2 * TC_STAGES + 4;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t q0 = blockIdx.x * TC_M;
@@ -167,6 +187,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       mbar_init(&tfull[b], 1);
       mbar_init(&tempty[b], 256);
     }
+    mbar_init(abar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // whole warp: allocate all 512 TMEM columns (two 128 x 256 fp32 accumulators)
@@ -181,16 +202,21 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      if (RESIDENT && ntiles > 0) {
+        mbar_expect_tx(abar, a.kblocks * A_BYTES);
+        for (uint32_t kb = 0; kb < a.kblocks; kb++)
+          tma_load_2d(res_a + size_t(kb) * A_BYTES, &map_q, static_cast<int>(kb * TC_KB), static_cast<int>(q0), abar);
+      }
       uint32_t it = 0;
       for (uint32_t t = 0; t < ntiles; t++) {
         const int r0 = static_cast<int>((tile_begin + t) * TC_N);
         for (uint32_t kb = 0; kb < a.kblocks; kb++, it++) {
           const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          uint8_t *sa = stage_base + size_t(s) * STAGE_BYTES;
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(sa, &map_q, static_cast<int>(kb * TC_KB), static_cast<int>(q0), &full[s]);
-          tma_load_2d(sa + A_BYTES, &map_x, static_cast<int>(kb * TC_KB), r0, &full[s]);
+          uint8_t *sa = stage_base + size_t(s) * kStage;
+          mbar_expect_tx(&full[s], kStage);
+          if (!RESIDENT) tma_load_2d(sa, &map_q, static_cast<int>(kb * TC_KB), static_cast<int>(q0), &full[s]);
+          tma_load_2d(sa + kBOff, &map_x, static_cast<int>(kb * TC_KB), r0, &full[s]);
         }
       }
     }
@@ -198,6 +224,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       uint32_t it = 0;
+      if (RESIDENT && ntiles > 0) mbar_wait(abar, 0);
       for (uint32_t t = 0; t < ntiles; t++) {
         const uint32_t b = t & 1u;
         mbar_wait(&tempty[b], ((t >> 1) & 1u) ^ 1u);
@@ -207,8 +234,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint8_t *sa = stage_base + size_t(s) * STAGE_BYTES;
-          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+          const uint8_t *sa = stage_base + size_t(s) * kStage;
+          const uint64_t da = make_smem_desc(RESIDENT ? res_a + size_t(kb) * A_BYTES : sa), db = make_smem_desc(sa + kBOff);
 #pragma unroll
           for (uint32_t k = 0; k < TC_KB / 8; k++)  // UMMA K = 8 tf32 = 32 bytes = 2 descriptor units
             tc_mma_tf32(tmem_d, da + 2 * k, db + 2 * k, kIdescTf32, (kb | k) != 0 ? 1u : 0u);
@@ -226,37 +253,48 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const float thr = qvalid ? a.thr[q] : -INFINITY;
     uint32_t *my = a.cand + (size_t(split) * a.nq + (qvalid ? q : 0)) * a.cap;
     const uint32_t lane_quadrant = (uint32_t(warp & 3) * 32u) << 16;
+    // per-row terms (||x||^2 or 0) of the next tile are fetched while the current one is scanned
+    float xn_next = ntiles > 0 ? (tile_begin * TC_N + e < a.n ? a.xnorm[tile_begin * TC_N + e] : INFINITY) : 0.f;
     for (uint32_t t = 0; t < ntiles; t++) {
       const uint32_t b = t & 1u;
       const uint64_t r0 = (tile_begin + t) * TC_N;
       float *sxb = sx + b * TC_N;
-      // per-row terms of this tile; rows past n can never pass the threshold
-      sxb[e] = r0 + e < a.n ? a.xnorm[r0 + e] : INFINITY;
+      sxb[e] = xn_next;  // rows past n carry +inf and can never pass the threshold
+      if (t + 1 < ntiles) {
+        const uint64_t rn = r0 + TC_N + e;
+        xn_next = rn < a.n ? a.xnorm[rn] : INFINITY;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull[b], (t >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (uint32_t c = 0; c < TC_N / 64; c++) {
-        const uint32_t col = half * (TC_N / 2) + c * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_quadrant + b * TC_N + col, v);
-        // cheap test first: the minimum approximate score of the 32 columns
-        float m = INFINITY;
+      for (uint32_t c = 0; c < TC_N / 128; c++) {
+        const uint32_t col = half * (TC_N / 2) + c * 64;
+        uint32_t v[2][32];
+        tmem_ld32_nowait(tmem_base + lane_quadrant + b * TC_N + col, v[0]);
+        tmem_ld32_nowait(tmem_base + lane_quadrant + b * TC_N + col + 32, v[1]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 s4 = *reinterpret_cast<const float4 *>(sxb + col + j);
-          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 0]), s4.x));
-          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 1]), s4.y));
-          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 2]), s4.z));
-          m = fminf(m, fmaf(a.alpha, __uint_as_float(v[j + 3]), s4.w));
-        }
-        if (m <= thr) {  // rare: some column survives
+        for (int h = 0; h < 2; h++) {
+          const uint32_t cc = col + h * 32;
+          // cheap test first: the minimum approximate score of the 32 columns
+          float m = INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const float s = fmaf(a.alpha, __uint_as_float(v[j]), sxb[col + j]);
-            if (s <= thr) {
-              const uint32_t pos = atomicAdd(&scnt[row], 1u);
-              if (pos < a.cap) my[pos] = static_cast<uint32_t>(r0 + col + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(sxb + cc + j);
+            m = fminf(m, fmaf(a.alpha, __uint_as_float(v[h][j + 0]), s4.x));
+            m = fminf(m, fmaf(a.alpha, __uint_as_float(v[h][j + 1]), s4.y));
+            m = fminf(m, fmaf(a.alpha, __uint_as_float(v[h][j + 2]), s4.z));
+            m = fminf(m, fmaf(a.alpha, __uint_as_float(v[h][j + 3]), s4.w));
+          }
+          if (m <= thr) {  // rare: some column survives
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float s = fmaf(a.alpha, __uint_as_float(v[h][j]), sxb[cc + j]);
+              if (s <= thr) {
+                const uint32_t pos = atomicAdd(&scnt[row], 1u);
+                if (pos < a.cap) my[pos] = static_cast<uint32_t>(r0 + cc + j);
+              }
             }
           }
         }
@@ -468,8 +506,22 @@ void bruteforce_topk_tc(int metric, const float *d_rows, uint64_t n, uint32_t di
   // ---- pass B: tcgen05 filter ---------------------------------------------------------------------
   const uint32_t qtiles = static_cast<uint32_t>((nq + TC_M - 1) / TC_M);
   const uint64_t total_tiles = (n + TC_N - 1) / TC_N;
-  uint32_t splits = std::max<uint32_t>(1, (uint32_t(sm_count) * 2 + qtiles - 1) / qtiles);
-  splits = static_cast<uint32_t>(std::min<uint64_t>(splits, total_tiles));
+  // one CTA per SM (197 KB of shared memory): pick the split count whose CTA total fills whole waves best
+  uint32_t splits = 1;
+  {
+    double best = -1.0;
+    const uint32_t smax = static_cast<uint32_t>(std::min<uint64_t>(total_tiles, std::max<uint32_t>(1, uint32_t(sm_count) * 8 / qtiles + 1)));
+    for (uint32_t sp = 1; sp <= smax; sp++) {
+      const uint64_t ctas = uint64_t(qtiles) * sp;
+      const uint64_t waves = (ctas + sm_count - 1) / sm_count;
+      const double eff = double(ctas) / double(waves * sm_count) - 0.002 * sp;  // mild preference for fewer splits
+      if (ctas >= uint64_t(sm_count) && eff > best) {
+        best = eff;
+        splits = sp;
+      }
+    }
+    if (best < 0) splits = smax;
+  }
   const uint32_t tiles_per_split = static_cast<uint32_t>((total_tiles + splits - 1) / splits);
   uint64_t expect = uint64_t(k) * ((n + sample - 1) / sample);  // survivors expected per query over all splits
   uint32_t cap = 256;
@@ -489,8 +541,13 @@ void bruteforce_topk_tc(int metric, const float *d_rows, uint64_t n, uint32_t di
   a.cand = cand.p;
   a.counts = counts.p;
   a.cap = cap;
-  AB_CUDA(cudaFuncSetAttribute(bf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM)));
-  bf_tc_kernel<<<dim3(qtiles, splits), TC_THREADS, TC_SMEM, s>>>(map_q, map_x, a);
+  if (a.kblocks <= 4) {
+    AB_CUDA(cudaFuncSetAttribute(bf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM)));
+    bf_tc_kernel<true><<<dim3(qtiles, splits), TC_THREADS, TC_SMEM, s>>>(map_q, map_x, a);
+  } else {
+    AB_CUDA(cudaFuncSetAttribute(bf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TC_SMEM)));
+    bf_tc_kernel<false><<<dim3(qtiles, splits), TC_THREADS, TC_SMEM, s>>>(map_q, map_x, a);
+  }
   AB_CUDA(cudaGetLastError());
   count_launch();
 
