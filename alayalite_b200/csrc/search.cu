@@ -46,29 +46,30 @@ struct WarpSmem {
 
 struct Visited {
   uint32_t *hash;
-  uint32_t hsize;  // any size (not a power of two): slot = mulhi(hash32, hsize)
+  uint32_t hmask;
+  int hshift;
   uint32_t *bitmap;
   bool spilled;
 };
 
-__device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t hsize) { return __umulhi(key * 0x9E3779B1u, hsize); }
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 0x9E3779B1u) >> shift; }
 
 // true if `key` was not yet in the set (and is now)
 __device__ __forceinline__ bool visit(const Visited &vs, uint32_t key) {
-  uint32_t slot = hash_slot(key, vs.hsize);
+  uint32_t slot = hash_slot(key, vs.hshift);
   if (!vs.spilled) {
     while (true) {
       const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
       if (old == kEmptyId) return true;
       if (old == key) return false;
-      slot = slot + 1 == vs.hsize ? 0u : slot + 1;
+      slot = (slot + 1) & vs.hmask;
     }
   }
   while (true) {  // spilled: the hash is frozen (read-only), new ids go to the bitmap
     const uint32_t cur = vs.hash[slot];
     if (cur == key) return false;
     if (cur == kEmptyId) break;
-    slot = slot + 1 == vs.hsize ? 0u : slot + 1;
+    slot = (slot + 1) & vs.hmask;
   }
   const uint32_t bit = 1u << (key & 31);
   const uint32_t old = atomicOr(&vs.bitmap[key >> 5], bit);
@@ -184,7 +185,7 @@ __device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpS
 // CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
 // CPL == 0 is the generic path for any space.
 template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
-__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? 4 : 1) beam_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? 3 : 1) beam_search_kernel(const SearchArgs a) {
   constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
   constexpr int MAXC = 8;
   constexpr int QREGS = FAST ? CPL : 1;
@@ -225,9 +226,10 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
 
   Visited vs;
   vs.hash = ws.hash;
-  vs.hsize = a.hash_size;
+  vs.hmask = a.hash_size - 1;
+  vs.hshift = 32 - (31 - __clz(a.hash_size));
   vs.bitmap = a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words;
-  const uint32_t hash_limit = a.hash_size - a.hash_size / 8;  // switch to the bitmap at 7/8 load
+  const uint32_t hash_limit = a.hash_size - a.hash_size / 4;  // switch to the bitmap at 3/4 load
   const int ef = static_cast<int>(a.ef);
 
   while (true) {
@@ -553,13 +555,13 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, uint32_t dim, uint
   (void)dim;
   SearchPlan p{};
   p.tpv = pick_tpv(nchunks);
-  // visited ids per query grow like ~22 * ef on the graphs measured; 28 * ef leaves head room below the 7/8 spill mark
-  uint32_t h = std::min<uint32_t>(16384u, std::max<uint32_t>(512u, (ef * 28u + 31u) / 32u * 32u));
+  uint32_t h = 512;
+  while (h < ef * 32u && h < 16384u) h <<= 1;
   const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;
   const size_t pool_bytes = round_up16(size_t(ef + 1) * 4);
   auto per_warp = [&](uint32_t hs) { return size_t(nchunks) * 16 + 2 * pool_bytes + size_t(hs) * 4 + 256; };
   // keep at least ~16 resident warps per SM: shrink the hash (queries then spill to the bitmap) if needed
-  while (h > 512 && (smem_limit - 2 * cta_fixed) / per_warp(h) < 16) h -= 32;
+  while (h > 512 && (smem_limit - 2 * cta_fixed) / per_warp(h) < 16) h >>= 1;
   p.hash_size = h;
   const size_t pw = per_warp(h);
   int warps_per_sm = static_cast<int>((smem_limit - 2 * cta_fixed - 2048) / pw);
