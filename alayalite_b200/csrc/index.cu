@@ -165,7 +165,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   if (nq == 0) return;
   const int quant = ix->params.quantization_type;
   const int nchunks = quant == AB_QUANT_NONE ? ix->raw_chunks : ix->code_chunks;
-  SearchPlan plan = plan_search(quant, nchunks, ix->table_len, ix->dim, ef, static_cast<uint32_t>(nq), ix->sm_count,
+  SearchPlan plan = plan_search(quant, nchunks, ix->table_len, ix->visit_ratio, ef, static_cast<uint32_t>(nq), ix->sm_count,
                                 ix->smem_limit);
   // private visited bitmaps, one per resident warp, all-zero between launches
   const size_t words = round_up((std::max<uint64_t>(ix->capacity, ix->n) + 31) / 32, 4);
@@ -218,6 +218,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   a.bitmap_words = words;
   a.stats = ix->w_stats.p;
   launch_search(quant, plan, a, stream);
+  ix->last_ef = ef;
 
   if (need_rerank) {
     RerankArgs r{};
@@ -272,6 +273,7 @@ static void search_host(ab_index *ix, const float *queries, uint64_t nq, uint32_
   AB_CUDA(cudaStreamSynchronize(s));
   for (int i = 0; i < 4; i++) ix->last_stats[i] = st[i];
   ix->last_stats[4] = nq;
+  if (nq >= 32 && ix->last_ef > 0) ix->visit_ratio = static_cast<float>(double(st[0]) / double(nq) / double(ix->last_ef));
 }
 
 }  // namespace ab

@@ -62,6 +62,8 @@ struct ab_index {
   size_t bitmap_words = 0;
   int bitmap_slots = 0;
   uint64_t last_stats[5] = {0, 0, 0, 0, 0};
+  uint32_t last_ef = 0;      // ef of the launch the device counters belong to
+  float visit_ratio = 0.f;   // visited ids per query / ef, from the last counters read back (sizes the visited hash)
 };
 
 namespace ab {

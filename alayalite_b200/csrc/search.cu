@@ -550,18 +550,23 @@ void launch_search_t(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
 
 }  // namespace
 
-SearchPlan plan_search(int quant, int nchunks, int table_len, uint32_t dim, uint32_t ef, uint32_t nq, int sm_count,
+SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, int sm_count,
                        size_t smem_limit) {
-  (void)dim;
   SearchPlan p{};
   p.tpv = pick_tpv(nchunks);
+  // size the hash so that the average query stays below the 3/4 spill mark: visited ids per query grow like
+  // ratio * ef, ratio ~ 21-24 on SIFT-like graphs and higher on harder data (taken from earlier searches)
+  const float ratio = std::max(24.0f, visit_ratio);
+  const uint32_t target = static_cast<uint32_t>(ratio * 1.34f * static_cast<float>(ef));
   uint32_t h = 512;
-  while (h < ef * 32u && h < 16384u) h <<= 1;
+  while (h < target && h < 16384u) h <<= 1;
   const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;
   const size_t pool_bytes = round_up16(size_t(ef + 1) * 4);
   auto per_warp = [&](uint32_t hs) { return size_t(nchunks) * 16 + 2 * pool_bytes + size_t(hs) * 4 + 256; };
   // keep at least ~16 resident warps per SM: shrink the hash (queries then spill to the bitmap) if needed
-  while (h > 512 && (smem_limit - 2 * cta_fixed) / per_warp(h) < 16) h >>= 1;
+  // prefer a hash that holds the whole visited set (~22 * ef ids) as long as 12 warps still fit per SM;
+  // below that, shrink it and let long queries continue in their global bitmap
+  while (h > 512 && (smem_limit - 2 * cta_fixed) / per_warp(h) < 12) h >>= 1;
   p.hash_size = h;
   const size_t pw = per_warp(h);
   int warps_per_sm = static_cast<int>((smem_limit - 2 * cta_fixed - 2048) / pw);

@@ -68,7 +68,8 @@ struct SearchPlan {
   int slots;          // ctas * warps_per_cta (bitmap slots needed)
 };
 
-SearchPlan plan_search(int quant, int nchunks, int table_len, uint32_t dim, uint32_t ef, uint32_t nq, int sm_count,
+// visit_ratio: visited ids per query divided by ef, measured on earlier searches of this index (0 = unknown)
+SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, int sm_count,
                        size_t smem_limit);
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
 void launch_rerank(const RerankArgs &args, int sm_count, cudaStream_t stream);
