@@ -467,7 +467,7 @@ int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64
     AB_CHECK(index != nullptr && d_queries && d_out_ids, AB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(index->mu);
     use_device(index);
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : index->stream;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, ordered with the caller's work
     index_search_device(index, d_queries, nq, topk, ef, rerank != 0, d_out_ids, d_out_dist, nullptr, nullptr, nullptr, s);
   });
 }

@@ -83,6 +83,9 @@ def test_config5_sharded_merge_equals_unsharded(cabi):
     half = n // 2
     gt = _gt(cabi, "l2", base, q, k)
     dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)  # one explicit stream for torch ops and the library's kernels
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
     g_ids = torch.empty((2, nq, k), dtype=torch.int32, device=dev)
     g_dist = torch.empty((2, nq, k), dtype=torch.float32, device=dev)
     out_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
@@ -92,7 +95,7 @@ def test_config5_sharded_merge_equals_unsharded(cabi):
         ids, dist = cabi.bruteforce_topk("l2", base[s * half:(s + 1) * half], q, k)
         g_ids[s] = torch.from_numpy((ids + s * half).astype(np.int32)).to(dev)
         g_dist[s] = torch.from_numpy(dist).to(dev)
-    cabi.merge_topk_device(g_dist.data_ptr(), g_ids.data_ptr(), 2, nq, k, out_ids.data_ptr(), out_dist.data_ptr())
+    cabi.merge_topk_device(g_dist.data_ptr(), g_ids.data_ptr(), 2, nq, k, out_ids.data_ptr(), out_dist.data_ptr(), sp)
     torch.cuda.synchronize()
     assert np.array_equal(out_ids.cpu().numpy().astype(np.uint32), gt)
     # (2) graph search per shard -> merge
@@ -106,9 +109,9 @@ def test_config5_sharded_merge_equals_unsharded(cabi):
     whole.fit(base, 100)
     for ef in (32, 64):
         for s, ix in enumerate(shards):
-            ix.batch_search_device(d_q.data_ptr(), nq, k, ef, g_ids[s].data_ptr(), g_dist[s].data_ptr())
+            ix.batch_search_device(d_q.data_ptr(), nq, k, ef, g_ids[s].data_ptr(), g_dist[s].data_ptr(), True, sp)
             g_ids[s] += s * half
-        cabi.merge_topk_device(g_dist.data_ptr(), g_ids.data_ptr(), 2, nq, k, out_ids.data_ptr(), out_dist.data_ptr())
+        cabi.merge_topk_device(g_dist.data_ptr(), g_ids.data_ptr(), 2, nq, k, out_ids.data_ptr(), out_dist.data_ptr(), sp)
         torch.cuda.synchronize()
         merged = out_ids.cpu().numpy().astype(np.uint32)
         assert np.all(np.diff(out_dist.cpu().numpy(), axis=1) >= 0)
