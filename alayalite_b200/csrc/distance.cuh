@@ -180,7 +180,7 @@ struct U64x2 {
 };
 __device__ __forceinline__ U64x2 ldg128_pairs(const void *p) {
   U64x2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+  asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
   return r;
 }
 __device__ __forceinline__ unsigned long long f2sub(unsigned long long x, unsigned long long y) {
@@ -247,14 +247,17 @@ __device__ __forceinline__ void raw_distance2(const uint8_t *r0, const uint8_t *
     a0 = raw_pairs_term<IP>(q[i], x0[i], a0);
     a1 = raw_pairs_term<IP>(q[i], x1[i], a1);
   }
-  float s0 = f2sum(a0), s1 = f2sum(a1);
+  // two sums across TPV lanes in log2(TPV) + 1 shuffles: the first exchange hands each lane the half it does
+  // not keep (even lanes keep candidate 0, odd lanes candidate 1), then one butterfly over the remaining bits
+  const float s0 = f2sum(a0), s1 = f2sum(a1);
+  const bool odd = lg & 1;
+  float s = (odd ? s1 : s0) + __shfl_xor_sync(0xFFFFFFFFu, odd ? s0 : s1, 1);
 #pragma unroll
-  for (int o = TPV / 2; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
-    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
-  }
-  d0 = IP ? -s0 : s0;
-  d1 = IP ? -s1 : s1;
+  for (int o = TPV / 2; o > 1; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  // lane 0 of the group holds candidate 0, lane 1 candidate 1: hand both to lane 0 (callers read lg == 0)
+  const float other = __shfl_down_sync(0xFFFFFFFFu, s, 1);
+  d0 = IP ? -s : s;
+  d1 = IP ? -other : other;
 }
 
 template <bool IP, int TPV, int CPL, bool EXACT>

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         ws.q_code[j] = static_cast<uint8_t>((first << 4) | second);
       }
     }
-    for (uint32_t i = lane; i < a.hash_size; i += 32) ws.hash[i] = kEmptyId;
+    for (uint32_t i = lane; i < a.hash_size / 4; i += 32) reinterpret_cast<uint4 *>(ws.hash)[i] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
     for (int i = lane; i <= ef; i += 32) {
       ws.pool_d[i] = 0.f;
       ws.pool_i[i] = 0u;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
 
     int size = 0, cur = 0;
     uint32_t nvis = 0;
-    unsigned long long ndc = 0, hops = 0, ndc_ov = 0;
+    uint32_t ndc = 0, hops = 0, ndc_ov = 0;  // per query: far below 2^32
     vs.spilled = false;
 
     // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
@@ -403,9 +403,9 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
     }
     if (lane == 0) {
-      atomicAdd(&a.stats[0], ndc);
-      atomicAdd(&a.stats[1], hops);
-      atomicAdd(&a.stats[2], ndc_ov);
+      atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
+      atomicAdd(&a.stats[1], static_cast<unsigned long long>(hops));
+      atomicAdd(&a.stats[2], static_cast<unsigned long long>(ndc_ov));
       if (vs.spilled) atomicAdd(&a.stats[3], 1ull);
     }
     __syncwarp();
