@@ -77,8 +77,11 @@ __device__ __forceinline__ bool visit(const Visited &vs, uint32_t key) {
 }
 
 // LinearPool::insert (query_utils.hpp:254-272); warp-collective, all arguments warp-uniform.
+// `expanded` inserts an entry that already carries the expanded flag (the hop that is about to run, see
+// the main loop): it never becomes the cursor, and pushes the cursor one slot right when it lands at or
+// before it.
 __device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, int &cur, int ef, float d,
-                                            uint32_t v, int lane) {
+                                            uint32_t v, int lane, bool expanded = false) {
   int pos = 0;  // upper bound: number of entries with dist <= d
   for (int base = 0; base < size; base += 32) {
     const int i = base + lane;
@@ -109,7 +112,17 @@ __device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, 
   }
   __syncwarp();
   size = nsize;
-  if (pos < cur) cur = pos;
+  if (expanded) {
+    if (pos <= cur) cur = min(cur + 1, nsize);
+  } else if (pos < cur) {
+    cur = pos;
+  }
+}
+
+// order-preserving map float -> uint32 (for warp-wide integer min)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
 // Evaluate the search-space distance of the candidate held by every lane with want == true.
@@ -333,13 +346,52 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     __syncwarp();
 
     // ---- best-first search on level 0 (graph_search_job.hpp:307-331) ---------------------------
-    while (cur < size) {
-      // LinearPool::pop (query_utils.hpp:284-293)
-      u = ws.pool_i[cur];
-      __syncwarp();
-      if (lane == 0) ws.pool_i[cur] = u | kCheckedBit;
-      __syncwarp();
-      {
+    // Same sequence of pops and inserts as the reference, scheduled differently: once the distances of a
+    // hop are known, the next node to expand is already determined -- the closer of the first un-expanded
+    // pool entry and the best accepted candidate (ties go to the pool entry, which upper-bound insertion
+    // would have placed first) -- so its adjacency row is requested first and the pool inserts of this hop
+    // run while that load is in flight. A candidate chosen this way is inserted with its expanded flag set.
+    u = ws.pool_i[0];  // LinearPool::pop of the entry node
+    __syncwarp();
+    if (lane == 0) ws.pool_i[0] = u | kCheckedBit;
+    cur = 1;
+    uint32_t v = a.adj[size_t(u) * kR + lane];
+    while (true) {
+      hops++;
+      const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
+      const int cnt = empties ? __ffs(empties) - 1 : kR;
+      if (!vs.spilled && nvis + kR > hash_limit) vs.spilled = true;
+      const bool is_new = lane < cnt && visit(vs, v);
+      const uint32_t newmask = __ballot_sync(kFull, is_new);
+      float d = FLT_MAX;
+      if (newmask) {
+        nvis += __popc(newmask);
+        d = AB_EVAL(v, is_new);
+      }
+      // A candidate that fails "d < worst" against a full pool now can only fail later too (worst never
+      // grows), so pre-filtering is exact.
+      const float worst = size == ef ? ws.pool_d[size - 1] : FLT_MAX;
+      const bool accept = is_new && (size < ef || d < worst);
+      uint32_t acc = __ballot_sync(kFull, accept);
+      const bool have_old = cur < size;
+      if (acc == 0 && !have_old) break;
+      int sel = -1;
+      if (acc) {
+        const uint32_t key = accept ? float_key(d) : 0xFFFFFFFFu;
+        const uint32_t kmin = __reduce_min_sync(kFull, key);
+        const int bl = __ffs(__ballot_sync(kFull, accept && key == kmin)) - 1;  // first neighbour attaining the minimum
+        const float best = __shfl_sync(kFull, d, bl);
+        if (!have_old || best < ws.pool_d[cur]) {
+          sel = bl;
+          u = __shfl_sync(kFull, v, bl);
+        }
+      }
+      if (sel < 0) {
+        // LinearPool::pop (query_utils.hpp:284-293)
+        u = ws.pool_i[cur];
+        __syncwarp();
+        if (lane == 0) ws.pool_i[cur] = u | kCheckedBit;
+        __syncwarp();
         int nxt = size;
         for (int base = cur + 1; base < size; base += 32) {
           const int i = base + lane;
@@ -351,38 +403,25 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         }
         cur = nxt;
       }
-      hops++;
-      // the closest un-expanded entry is the likely next hop: pull its adjacency row towards L2 now
-      if (lane == 0 && cur < size) {
-        const uint32_t nx = ws.pool_i[cur] & kIdMask;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
-      }
+      const uint32_t v_next = a.adj[size_t(u) * kR + lane];
 
-      const uint32_t v = a.adj[size_t(u) * kR + lane];
-      const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
-      const int cnt = empties ? __ffs(empties) - 1 : kR;
-      if (!vs.spilled && nvis + kR > hash_limit) vs.spilled = true;
-      const bool is_new = lane < cnt && visit(vs, v);
-      const uint32_t newmask = __ballot_sync(kFull, is_new);
-      const int nnew = __popc(newmask);
-      if (nnew == 0) continue;
-      nvis += nnew;
-      ndc += nnew;
-      const float d = AB_EVAL(v, is_new);
-
-      // inserts in neighbour order. A candidate that fails "d < worst" against a full pool now can
-      // only fail later too (worst never grows), so pre-filtering is exact.
-      const float worst = size == ef ? ws.pool_d[size - 1] : FLT_MAX;
-      uint32_t acc = __ballot_sync(kFull, is_new && (size < ef || d < worst));
+      // inserts in neighbour order
       while (acc) {
         const int j = __ffs(acc) - 1;
         acc &= acc - 1;
         const float dj = __shfl_sync(kFull, d, j);
         const uint32_t vj = __shfl_sync(kFull, v, j);
         if (size == ef && dj >= ws.pool_d[size - 1]) continue;
-        pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, dj, vj, lane);
+        pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, dj, j == sel ? (vj | kCheckedBit) : vj, lane, j == sel);
       }
+      // the closest un-expanded entry is the likely hop after this one: pull its adjacency row towards L2
+      if (lane == 0 && cur < size) {
+        const uint32_t nx = ws.pool_i[cur] & kIdMask;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
+      }
+      v = v_next;
     }
+    ndc = nvis - 1;
 
     // ---- results ----------------------------------------------------------------------------
     for (uint32_t i = lane; i < a.topk; i += 32) {
