@@ -241,6 +241,7 @@ __device__ __forceinline__ void raw_distance2(const uint8_t *r0, const uint8_t *
       x0[i].a = x0[i].b = x1[i].a = x1[i].b = 0ull;
     }
   }
+  __syncwarp();  // scheduling fence: keeps ptxas from sinking the last loads below the first arithmetic
   unsigned long long a0 = 0ull, a1 = 0ull;
 #pragma unroll
   for (int i = 0; i < CPL; i++) {

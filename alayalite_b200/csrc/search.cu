@@ -37,42 +37,42 @@ constexpr int kR = 32;  // level-0 degree (reference: params_.max_nbrs_ is alway
 struct WarpSmem {
   float *q_raw;       // raw query (raw space only)
   uint8_t *q_code;    // encoded query (SQ only)
-  float *pool_d;      // [ef + 1]
-  uint32_t *pool_i;   // [ef + 1]
+  uint2 *pool;        // [ef + 1] entries {distance bits, id | expanded flag}
   uint32_t *hash;     // [hash_size]
   uint32_t *cand;     // [32] candidate ids of the current hop, compacted
   float *cdist;       // [32] their distances
 };
 
+// Visited set of one query. Derived values (mask, shift, the warp's bitmap) are recomputed from the
+// kernel arguments where needed instead of living in registers across the hot loop.
 struct Visited {
   uint32_t *hash;
-  uint32_t hmask;
-  int hshift;
-  uint32_t *bitmap;
   bool spilled;
 };
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 0x9E3779B1u) >> shift; }
 
 // true if `key` was not yet in the set (and is now)
-__device__ __forceinline__ bool visit(const Visited &vs, uint32_t key) {
-  uint32_t slot = hash_slot(key, vs.hshift);
+__device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, uint32_t key) {
+  const uint32_t hmask = a.hash_size - 1;
+  uint32_t slot = hash_slot(key, a.hash_shift);
   if (!vs.spilled) {
     while (true) {
       const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
       if (old == kEmptyId) return true;
       if (old == key) return false;
-      slot = (slot + 1) & vs.hmask;
+      slot = (slot + 1) & hmask;
     }
   }
   while (true) {  // spilled: the hash is frozen (read-only), new ids go to the bitmap
     const uint32_t cur = vs.hash[slot];
     if (cur == key) return false;
     if (cur == kEmptyId) break;
-    slot = (slot + 1) & vs.hmask;
+    slot = (slot + 1) & hmask;
   }
+  uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
   const uint32_t bit = 1u << (key & 31);
-  const uint32_t old = atomicOr(&vs.bitmap[key >> 5], bit);
+  const uint32_t old = atomicOr(&bitmap[key >> 5], bit);
   return (old & bit) == 0;
 }
 
@@ -80,12 +80,12 @@ __device__ __forceinline__ bool visit(const Visited &vs, uint32_t key) {
 // `expanded` inserts an entry that already carries the expanded flag (the hop that is about to run, see
 // the main loop): it never becomes the cursor, and pushes the cursor one slot right when it lands at or
 // before it.
-__device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, int &cur, int ef, float d,
-                                            uint32_t v, int lane, bool expanded = false) {
+__device__ __forceinline__ void pool_insert(uint2 *pool, int &size, int &cur, int ef, float d, uint32_t v, int lane,
+                                            bool expanded = false) {
   int pos = 0;  // upper bound: number of entries with dist <= d
   for (int base = 0; base < size; base += 32) {
     const int i = base + lane;
-    const uint32_t b = __ballot_sync(kFull, i < size && pd[i] <= d);
+    const uint32_t b = __ballot_sync(kFull, i < size && __uint_as_float(pool[i].x) <= d);
     pos += __popc(b);
     if (b != kFull) break;
   }
@@ -93,23 +93,13 @@ __device__ __forceinline__ void pool_insert(float *pd, uint32_t *pi, int &size, 
   for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 > pos; base -= 32) {
     const int i = base + lane;
     const bool mv = i > pos && i < nsize;
-    float td = 0.f;
-    uint32_t ti = 0;
-    if (mv) {
-      td = pd[i - 1];
-      ti = pi[i - 1];
-    }
+    uint2 t = make_uint2(0u, 0u);
+    if (mv) t = pool[i - 1];
     __syncwarp();
-    if (mv) {
-      pd[i] = td;
-      pi[i] = ti;
-    }
+    if (mv) pool[i] = t;
     __syncwarp();
   }
-  if (lane == 0) {
-    pd[pos] = d;
-    pi[pos] = v;
-  }
+  if (lane == 0) pool[pos] = make_uint2(__float_as_uint(d), v);
   __syncwarp();
   size = nsize;
   if (expanded) {
@@ -212,17 +202,16 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
   float *s_vmin = s_scale + (QUANT != AB_QUANT_NONE ? a.table_len : 0);
   size_t off = (QUANT != AB_QUANT_NONE ? size_t(a.table_len) * 8 : 0);
   const size_t q_bytes = size_t(a.nchunks) * 16;
-  const size_t pool_bytes = round_up16(size_t(a.ef + 1) * 4);
-  const size_t per_warp = q_bytes + 2 * pool_bytes + size_t(a.hash_size) * 4 + 256;
+  const size_t pool_bytes = round_up16(size_t(a.ef + 1) * 8);
+  const size_t per_warp = 256 + q_bytes + pool_bytes + size_t(a.hash_size) * 4;
   uint8_t *wbase = smem + off + size_t(warp) * per_warp;
   WarpSmem ws;
-  ws.q_raw = reinterpret_cast<float *>(wbase);
-  ws.q_code = wbase;
-  ws.pool_d = reinterpret_cast<float *>(wbase + q_bytes);
-  ws.pool_i = reinterpret_cast<uint32_t *>(wbase + q_bytes + pool_bytes);
-  ws.hash = reinterpret_cast<uint32_t *>(wbase + q_bytes + 2 * pool_bytes);
-  ws.cand = ws.hash + a.hash_size;
-  ws.cdist = reinterpret_cast<float *>(ws.cand + 32);
+  ws.cand = reinterpret_cast<uint32_t *>(wbase);
+  ws.cdist = reinterpret_cast<float *>(wbase + 128);
+  ws.q_raw = reinterpret_cast<float *>(wbase + 256);
+  ws.q_code = wbase + 256;
+  ws.pool = reinterpret_cast<uint2 *>(wbase + 256 + q_bytes);
+  ws.hash = reinterpret_cast<uint32_t *>(wbase + 256 + q_bytes + pool_bytes);
 
   if (QUANT != AB_QUANT_NONE) {
     for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) {
@@ -239,10 +228,6 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
 
   Visited vs;
   vs.hash = ws.hash;
-  vs.hmask = a.hash_size - 1;
-  vs.hshift = 32 - (31 - __clz(a.hash_size));
-  vs.bitmap = a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words;
-  const uint32_t hash_limit = a.hash_size - a.hash_size / 4;  // switch to the bitmap at 3/4 load
   const int ef = static_cast<int>(a.ef);
 
   while (true) {
@@ -290,8 +275,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     }
     for (uint32_t i = lane; i < a.hash_size / 4; i += 32) reinterpret_cast<uint4 *>(ws.hash)[i] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
     for (int i = lane; i <= ef; i += 32) {
-      ws.pool_d[i] = 0.f;
-      ws.pool_i[i] = 0u;
+      ws.pool[i] = make_uint2(0u, 0u);
     }
     __syncwarp();
 
@@ -340,8 +324,9 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         }
       }
     }
-    pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, cur_d, u, lane);
-    if (lane == 0) visit(vs, u);
+    if (lane == 0) atomicAdd(&a.stats[2], static_cast<unsigned long long>(ndc_ov));
+    pool_insert(ws.pool, size, cur, ef, cur_d, u, lane);
+    if (lane == 0) visit(a, vs, u);
     nvis = 1;
     __syncwarp();
 
@@ -351,17 +336,17 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     // pool entry and the best accepted candidate (ties go to the pool entry, which upper-bound insertion
     // would have placed first) -- so its adjacency row is requested first and the pool inserts of this hop
     // run while that load is in flight. A candidate chosen this way is inserted with its expanded flag set.
-    u = ws.pool_i[0];  // LinearPool::pop of the entry node
+    u = ws.pool[0].y;  // LinearPool::pop of the entry node
     __syncwarp();
-    if (lane == 0) ws.pool_i[0] = u | kCheckedBit;
+    if (lane == 0) ws.pool[0].y = u | kCheckedBit;
     cur = 1;
     uint32_t v = a.adj[size_t(u) * kR + lane];
     while (true) {
       hops++;
       const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
       const int cnt = empties ? __ffs(empties) - 1 : kR;
-      if (!vs.spilled && nvis + kR > hash_limit) vs.spilled = true;
-      const bool is_new = lane < cnt && visit(vs, v);
+      if (!vs.spilled && nvis + kR > a.hash_limit) vs.spilled = true;
+      const bool is_new = lane < cnt && visit(a, vs, v);
       const uint32_t newmask = __ballot_sync(kFull, is_new);
       float d = FLT_MAX;
       if (newmask) {
@@ -370,7 +355,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       }
       // A candidate that fails "d < worst" against a full pool now can only fail later too (worst never
       // grows), so pre-filtering is exact.
-      const float worst = size == ef ? ws.pool_d[size - 1] : FLT_MAX;
+      const float worst = size == ef ? __uint_as_float(ws.pool[size - 1].x) : FLT_MAX;
       const bool accept = is_new && (size < ef || d < worst);
       uint32_t acc = __ballot_sync(kFull, accept);
       const bool have_old = cur < size;
@@ -381,21 +366,21 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         const uint32_t kmin = __reduce_min_sync(kFull, key);
         const int bl = __ffs(__ballot_sync(kFull, accept && key == kmin)) - 1;  // first neighbour attaining the minimum
         const float best = __shfl_sync(kFull, d, bl);
-        if (!have_old || best < ws.pool_d[cur]) {
+        if (!have_old || best < __uint_as_float(ws.pool[cur].x)) {
           sel = bl;
           u = __shfl_sync(kFull, v, bl);
         }
       }
       if (sel < 0) {
         // LinearPool::pop (query_utils.hpp:284-293)
-        u = ws.pool_i[cur];
+        u = ws.pool[cur].y;
         __syncwarp();
-        if (lane == 0) ws.pool_i[cur] = u | kCheckedBit;
+        if (lane == 0) ws.pool[cur].y = u | kCheckedBit;
         __syncwarp();
         int nxt = size;
         for (int base = cur + 1; base < size; base += 32) {
           const int i = base + lane;
-          const uint32_t b = __ballot_sync(kFull, i < size && (ws.pool_i[i] & kCheckedBit) == 0);
+          const uint32_t b = __ballot_sync(kFull, i < size && (ws.pool[i].y & kCheckedBit) == 0);
           if (b) {
             nxt = base + __ffs(b) - 1;
             break;
@@ -411,12 +396,12 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         acc &= acc - 1;
         const float dj = __shfl_sync(kFull, d, j);
         const uint32_t vj = __shfl_sync(kFull, v, j);
-        if (size == ef && dj >= ws.pool_d[size - 1]) continue;
-        pool_insert(ws.pool_d, ws.pool_i, size, cur, ef, dj, j == sel ? (vj | kCheckedBit) : vj, lane, j == sel);
+        if (size == ef && dj >= __uint_as_float(ws.pool[size - 1].x)) continue;
+        pool_insert(ws.pool, size, cur, ef, dj, j == sel ? (vj | kCheckedBit) : vj, lane, j == sel);
       }
       // the closest un-expanded entry is the likely hop after this one: pull its adjacency row towards L2
       if (lane == 0 && cur < size) {
-        const uint32_t nx = ws.pool_i[cur] & kIdMask;
+        const uint32_t nx = ws.pool[cur].y & kIdMask;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
       }
       v = v_next;
@@ -426,25 +411,24 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     // ---- results ----------------------------------------------------------------------------
     for (uint32_t i = lane; i < a.topk; i += 32) {
       const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
-      a.out_ids[size_t(qi) * a.topk + i] = in ? (ws.pool_i[i] & kIdMask) : 0u;
-      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = in ? ws.pool_d[i] : 0.f;
+      a.out_ids[size_t(qi) * a.topk + i] = in ? (ws.pool[i].y & kIdMask) : 0u;
+      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = in ? __uint_as_float(ws.pool[i].x) : 0.f;
     }
     if (a.pool_ids) {
       for (int i = lane; i < ef; i += 32) {
-        a.pool_ids[size_t(qi) * a.ef + i] = i < size ? (ws.pool_i[i] & kIdMask) : 0u;
-        a.pool_dist[size_t(qi) * a.ef + i] = i < size ? ws.pool_d[i] : 0.f;
+        a.pool_ids[size_t(qi) * a.ef + i] = i < size ? (ws.pool[i].y & kIdMask) : 0u;
+        a.pool_dist[size_t(qi) * a.ef + i] = i < size ? __uint_as_float(ws.pool[i].x) : 0.f;
       }
       if (lane == 0) a.pool_sizes[qi] = size;
     }
     if (vs.spilled) {
       // give the private bitmap back all-zero (the reference allocates + zeroes one per query)
-      uint4 *bm = reinterpret_cast<uint4 *>(vs.bitmap);
+      uint4 *bm = reinterpret_cast<uint4 *>(a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words);
       for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
     }
     if (lane == 0) {
       atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
       atomicAdd(&a.stats[1], static_cast<unsigned long long>(hops));
-      atomicAdd(&a.stats[2], static_cast<unsigned long long>(ndc_ov));
       if (vs.spilled) atomicAdd(&a.stats[3], 1ull);
     }
     __syncwarp();
@@ -600,8 +584,8 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   uint32_t h = 512;
   while (h < target && h < 16384u) h <<= 1;
   const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;
-  const size_t pool_bytes = round_up16(size_t(ef + 1) * 4);
-  auto per_warp = [&](uint32_t hs) { return size_t(nchunks) * 16 + 2 * pool_bytes + size_t(hs) * 4 + 256; };
+  const size_t pool_bytes = round_up16(size_t(ef + 1) * 8);
+  auto per_warp = [&](uint32_t hs) { return 256 + size_t(nchunks) * 16 + pool_bytes + size_t(hs) * 4; };
   // keep at least ~16 resident warps per SM: shrink the hash (queries then spill to the bitmap) if needed
   // prefer a hash that holds the whole visited set (~22 * ef ids) as long as 12 warps still fit per SM;
   // below that, shrink it and let long queries continue in their global bitmap
@@ -622,7 +606,12 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   return p;
 }
 
-void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream) {
+void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args_in, cudaStream_t stream) {
+  SearchArgs args = args_in;
+  int lg = 0;
+  while ((1u << lg) < args.hash_size) lg++;
+  args.hash_shift = 32 - lg;
+  args.hash_limit = args.hash_size - args.hash_size / 4;
   const bool ip = args.metric != AB_METRIC_L2;
   if (quant == AB_QUANT_NONE) {
     ip ? launch_search_t<AB_QUANT_NONE, true>(plan, args, stream) : launch_search_t<AB_QUANT_NONE, false>(plan, args, stream);

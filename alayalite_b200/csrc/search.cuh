@@ -39,6 +39,8 @@ struct SearchArgs {
   // scheduling + visited set
   uint32_t *work_counter;       // zeroed before launch
   uint32_t hash_size;           // shared-memory hash entries per warp (power of two)
+  int hash_shift;               // 32 - log2(hash_size)      } filled in by launch_search
+  uint32_t hash_limit;          // spill to the bitmap past this many ids (3/4 load)
   uint32_t *bitmaps;            // [slots, bitmap_words] all zero between launches
   size_t bitmap_words;
   unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, spilled queries}
