@@ -321,7 +321,7 @@ void build_layer(ab_index *ix, const LayerJob &job, uint32_t efc, uint32_t max_b
     AB_CUDA(cudaMemsetAsync(w.counter.p, 0, sizeof(uint32_t), s));
     SearchArgs a{};
     a.rows = job.view.rows;
-    a.row_stride = job.view.stride;
+    a.row_stride = static_cast<uint32_t>(job.view.stride);
     a.nchunks = job.view.nchunks;
     a.adj = job.view.adj;
     a.ov_off = descend ? job.ov_off : nullptr;

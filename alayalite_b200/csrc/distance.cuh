@@ -230,7 +230,7 @@ __device__ __forceinline__ void load_query_regs(const float *q_smem, int nchunks
 // rows r0 / r1 already point at this lane's first chunk (row + lg * 16)
 template <bool IP, int TPV, int CPL, bool EXACT>
 __device__ __forceinline__ void raw_distance2(const uint8_t *r0, const uint8_t *r1, const U64x2 (&q)[CPL], int nchunks, int lg,
-                                              float &d0, float &d1) {
+                                              float &d) {
   U64x2 x0[CPL], x1[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; i++) {
@@ -255,10 +255,8 @@ __device__ __forceinline__ void raw_distance2(const uint8_t *r0, const uint8_t *
   float s = (odd ? s1 : s0) + __shfl_xor_sync(0xFFFFFFFFu, odd ? s0 : s1, 1);
 #pragma unroll
   for (int o = TPV / 2; o > 1; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-  // lane 0 of the group holds candidate 0, lane 1 candidate 1: hand both to lane 0 (callers read lg == 0)
-  const float other = __shfl_down_sync(0xFFFFFFFFu, s, 1);
-  d0 = IP ? -s : s;
-  d1 = IP ? -other : other;
+  // even lanes of the group now hold candidate 0's distance, odd lanes candidate 1's
+  d = IP ? -s : s;
 }
 
 template <bool IP, int TPV, int CPL, bool EXACT>

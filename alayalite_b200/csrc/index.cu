@@ -184,7 +184,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
 
   SearchArgs a{};
   a.rows = quant == AB_QUANT_NONE ? reinterpret_cast<const uint8_t *>(ix->raw.p) : ix->codes.p;
-  a.row_stride = quant == AB_QUANT_NONE ? size_t(ix->raw_stride) * 4 : ix->code_stride;
+  a.row_stride = static_cast<uint32_t>(quant == AB_QUANT_NONE ? size_t(ix->raw_stride) * 4 : ix->code_stride);
   a.nchunks = nchunks;
   a.table_len = ix->table_len;
   a.qmin = ix->qmin.p;

@@ -52,28 +52,44 @@ struct Visited {
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 0x9E3779B1u) >> shift; }
 
-// true if `key` was not yet in the set (and is now)
-__device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, uint32_t key) {
+// Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
+// The probe loop is driven by a warp vote, so the warp stays converged (a per-lane probe loop leaves the
+// lanes split under independent thread scheduling, and every later warp-level primitive then takes the
+// compiler's slow divergent path).
+__device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, uint32_t key, bool active) {
   const uint32_t hmask = a.hash_size - 1;
   uint32_t slot = hash_slot(key, a.hash_shift);
+  bool is_new = false;
+  bool pending = active;
   if (!vs.spilled) {
-    while (true) {
-      const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
-      if (old == kEmptyId) return true;
-      if (old == key) return false;
+    while (__any_sync(kFull, pending)) {
+      if (pending) {
+        const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
+        is_new = old == kEmptyId;
+        pending = !(is_new || old == key);
+        slot = (slot + 1) & hmask;
+      }
+    }
+    return is_new;
+  }
+  // spilled: the hash is frozen (read-only), new ids go to the warp's bitmap in global memory
+  bool absent = false;
+  while (__any_sync(kFull, pending)) {
+    if (pending) {
+      const uint32_t cur = vs.hash[slot];
+      absent = cur == kEmptyId;
+      pending = !(absent || cur == key);
       slot = (slot + 1) & hmask;
     }
   }
-  while (true) {  // spilled: the hash is frozen (read-only), new ids go to the bitmap
-    const uint32_t cur = vs.hash[slot];
-    if (cur == key) return false;
-    if (cur == kEmptyId) break;
-    slot = (slot + 1) & hmask;
+  if (absent) {
+    uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
+    const uint32_t bit = 1u << (key & 31);
+    const uint32_t old = atomicOr(&bitmap[key >> 5], bit);
+    is_new = (old & bit) == 0;
   }
-  uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
-  const uint32_t bit = 1u << (key & 31);
-  const uint32_t old = atomicOr(&bitmap[key >> 5], bit);
-  return (old & bit) == 0;
+  __syncwarp();
+  return is_new;
 }
 
 // LinearPool::insert (query_utils.hpp:254-272); warp-collective, all arguments warp-uniform.
@@ -131,12 +147,8 @@ __device__ __forceinline__ float eval_lanes(const SearchArgs &a, const WarpSmem 
     const int k = base + g;
     const bool act = k < cnt;
     const uint32_t cv = act ? ws.cand[k] : 0u;
-    float d = row_distance<QUANT, IP, TPV, MAXC>(a.rows + size_t(cv) * a.row_stride, a.nchunks, lg, qs, act);
-    if (act && lg == 0) {
-      // RawSpace::QueryComputer returns FLT_MAX for tombstoned rows (raw_space.hpp:297-304)
-      if (QUANT == AB_QUANT_NONE && a.valid != nullptr && ((a.valid[cv >> 5] >> (cv & 31)) & 1u) == 0) d = FLT_MAX;
-      ws.cdist[k] = d;
-    }
+    float d = row_distance<QUANT, IP, TPV, MAXC>(a.rows + size_t(cv) * size_t(a.row_stride), a.nchunks, lg, qs, act);
+    if (act && lg == 0) ws.cdist[k] = d;
   }
   __syncwarp();
   const float out = want ? ws.cdist[rank] : FLT_MAX;
@@ -161,22 +173,19 @@ __device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpS
     const int k0 = base + g, k1 = k0 + G;
     const bool act0 = k0 < cnt, act1 = k1 < cnt;
     const uint32_t c0 = ws.cand[act0 ? k0 : 0];
-    float d0, d1 = 0.f;
+    float d0;
     uint32_t c1 = c0;
     if (cnt - base > G) {  // warp-uniform: a second candidate exists for at least one group
       c1 = ws.cand[act1 ? k1 : 0];
       raw_distance2<IP, TPV, CPL, EXACT>(lane_base + size_t(c0) * a.row_stride, lane_base + size_t(c1) * a.row_stride, q,
-                                         a.nchunks, lg, d0, d1);
-    } else {
+                                         a.nchunks, lg, d0);
+    } else {  // every lane of the group gets the sum
       d0 = raw_distance1<IP, TPV, CPL, EXACT>(lane_base + size_t(c0) * a.row_stride, q, a.nchunks, lg);
     }
-    if (lg == 0) {
-      if (a.valid != nullptr) {  // RawSpace::QueryComputer: FLT_MAX for tombstoned rows (raw_space.hpp:297-304)
-        if (((a.valid[c0 >> 5] >> (c0 & 31)) & 1u) == 0) d0 = FLT_MAX;
-        if (((a.valid[c1 >> 5] >> (c1 & 31)) & 1u) == 0) d1 = FLT_MAX;
-      }
-      if (act0) ws.cdist[k0] = d0;
-      if (act1) ws.cdist[k1] = d1;
+    // lane 0 of a group ends up with the first candidate's distance, lane 1 with the second's
+    if (lg < 2) {
+      const int k = lg ? k1 : k0;
+      if (k < cnt) ws.cdist[k] = d0;
     }
   }
   __syncwarp();
@@ -194,7 +203,8 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
   constexpr int QREGS = FAST ? CPL : 1;
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = lane_id();
-  const int warp = threadIdx.x >> 5;
+  // redux lands in a uniform register: the compiler then knows every per-warp address below is warp-uniform
+  const int warp = static_cast<int>(__reduce_min_sync(kFull, threadIdx.x >> 5));
   const int warps = blockDim.x >> 5;
 
   // ---- carve shared memory: CTA-wide tables, then one region per warp -------------------------
@@ -231,9 +241,10 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
   const int ef = static_cast<int>(a.ef);
 
   while (true) {
-    uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(a.work_counter, 1u);
-    qi = __shfl_sync(kFull, qi, 0);
+    if (lane == 0) ws.cand[0] = atomicAdd(a.work_counter, 1u);
+    __syncwarp();
+    const uint32_t qi = ws.cand[0];
+    __syncwarp();
     if (qi >= a.nq) break;
     const float *qg = a.queries + size_t(a.q_ids ? a.q_ids[qi] : qi) * a.q_stride;
 
@@ -288,9 +299,31 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     uint32_t u = a.ep;
     U64x2 qreg[QREGS];
     if (FAST) load_query_regs<TPV, QREGS, EXACT>(ws.q_raw, a.nchunks, lane % TPV, qreg);
-#define AB_EVAL(ID, WANT) (FAST ? eval_lanes_raw<IP, TPV, QREGS, EXACT>(a, ws, qreg, ID, WANT, lane) : eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, ID, WANT, lane))
-    float cur_d = AB_EVAL(u, lane == 0);
-    cur_d = __shfl_sync(kFull, cur_d, 0);
+    // distance of the candidate in every lane with WANT; afterwards ws.cand / ws.cdist hold the wanted ids and
+    // distances compacted in lane order. Warp-uniform values are re-read from there (uniform shared-memory
+    // loads) rather than shuffled, which keeps the control flow provably convergent for the compiler.
+    auto eval = [&](uint32_t id, bool want) -> float {
+      float dd;
+      if (FAST) {
+        dd = eval_lanes_raw<IP, TPV, QREGS, EXACT>(a, ws, qreg, id, want, lane);
+      } else {
+        dd = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, id, want, lane);
+      }
+      if (QUANT == AB_QUANT_NONE && a.valid != nullptr) {
+        // RawSpace::QueryComputer returns FLT_MAX for tombstoned rows (raw_space.hpp:297-304)
+        const uint32_t wm = __ballot_sync(kFull, want);
+        if (want && ((a.valid[id >> 5] >> (id & 31)) & 1u) == 0) {
+          dd = FLT_MAX;
+          ws.cdist[__popc(wm & ((1u << lane) - 1))] = dd;
+        }
+        __syncwarp();
+      }
+      return dd;
+    };
+#define AB_EVAL(ID, WANT) eval(ID, WANT)
+    AB_EVAL(u, lane == 0);
+    float cur_d = ws.cdist[0];
+    __syncwarp();
     ndc_ov += 1;
     if (a.ov_off != nullptr) {
       for (int level = static_cast<int>(a.ep_level); level > 0; --level) {
@@ -302,31 +335,27 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
           const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
           const int cnt = empties ? __ffs(empties) - 1 : kR;
           const bool want = lane < cnt;
-          float d = AB_EVAL(v, want);
+          const float d = AB_EVAL(v, want);
           ndc_ov += cnt;
           // sequential "if (dist < cur_dist)" scan == first index attaining the minimum, if < cur_d
-          float best = want ? d : FLT_MAX;
-          int best_lane = lane;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(kFull, best, o);
-            const int ol = __shfl_xor_sync(kFull, best_lane, o);
-            if (od < best || (od == best && ol < best_lane)) {
-              best = od;
-              best_lane = ol;
+          if (cnt > 0) {
+            const uint32_t key = want ? float_key(d) : 0xFFFFFFFFu;
+            const uint32_t kmin = __reduce_min_sync(kFull, key);
+            const int bl = __ffs(__ballot_sync(kFull, want && key == kmin)) - 1;  // want lanes are 0..cnt-1: rank == lane
+            const float best = ws.cdist[bl];
+            if (best < cur_d) {
+              cur_d = best;
+              u = ws.cand[bl];
+              changed = true;
             }
           }
-          if (cnt > 0 && best < cur_d) {
-            cur_d = best;
-            u = __shfl_sync(kFull, v, best_lane);
-            changed = true;
-          }
+          __syncwarp();
         }
       }
     }
     if (lane == 0) atomicAdd(&a.stats[2], static_cast<unsigned long long>(ndc_ov));
     pool_insert(ws.pool, size, cur, ef, cur_d, u, lane);
-    if (lane == 0) visit(a, vs, u);
+    visit(a, vs, u, lane == 0);
     nvis = 1;
     __syncwarp();
 
@@ -346,7 +375,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
       const int cnt = empties ? __ffs(empties) - 1 : kR;
       if (!vs.spilled && nvis + kR > a.hash_limit) vs.spilled = true;
-      const bool is_new = lane < cnt && visit(a, vs, v);
+      const bool is_new = visit(a, vs, v, lane < cnt);
       const uint32_t newmask = __ballot_sync(kFull, is_new);
       float d = FLT_MAX;
       if (newmask) {
@@ -365,10 +394,10 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         const uint32_t key = accept ? float_key(d) : 0xFFFFFFFFu;
         const uint32_t kmin = __reduce_min_sync(kFull, key);
         const int bl = __ffs(__ballot_sync(kFull, accept && key == kmin)) - 1;  // first neighbour attaining the minimum
-        const float best = __shfl_sync(kFull, d, bl);
-        if (!have_old || best < __uint_as_float(ws.pool[cur].x)) {
+        const int rb = __popc(newmask & ((1u << bl) - 1));
+        if (!have_old || ws.cdist[rb] < __uint_as_float(ws.pool[cur].x)) {
           sel = bl;
-          u = __shfl_sync(kFull, v, bl);
+          u = ws.cand[rb];
         }
       }
       if (sel < 0) {
@@ -394,8 +423,9 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       while (acc) {
         const int j = __ffs(acc) - 1;
         acc &= acc - 1;
-        const float dj = __shfl_sync(kFull, d, j);
-        const uint32_t vj = __shfl_sync(kFull, v, j);
+        const int rj = __popc(newmask & ((1u << j) - 1));
+        const float dj = ws.cdist[rj];
+        const uint32_t vj = ws.cand[rj];
         if (size == ef && dj >= __uint_as_float(ws.pool[size - 1].x)) continue;
         pool_insert(ws.pool, size, cur, ef, dj, j == sel ? (vj | kCheckedBit) : vj, lane, j == sel);
       }

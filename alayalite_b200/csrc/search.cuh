@@ -8,7 +8,7 @@ namespace ab {
 struct SearchArgs {
   // search space rows: raw floats or SQ codes, row stride in bytes (multiple of 64)
   const uint8_t *rows;
-  size_t row_stride;
+  uint32_t row_stride;
   int nchunks;         // 16-byte chunks per row that carry data
   int table_len;       // entries in the dequantisation tables (SQ only)
   const float *qmin;   // [dim] quantizer min (SQ only)
