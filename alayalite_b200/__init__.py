@@ -9,10 +9,10 @@ fallback: the first use of the API fails loudly if they are missing.
 
 import importlib as _importlib
 
-__all__ = ["Client", "Index", "IndexParams", "load_fvecs", "load_ivecs", "calc_recall", "calc_gt"]
+__all__ = ["Client", "Collection", "Index", "IndexParams", "load_fvecs", "load_ivecs", "calc_recall", "calc_gt"]
 __version__ = "0.1.0"
 
-_WHERE = {"Client": ".client", "Index": ".index", "IndexParams": ".schema", "calc_gt": ".utils", "calc_recall": ".utils",
+_WHERE = {"Client": ".client", "Collection": ".collection", "Index": ".index", "IndexParams": ".schema", "calc_gt": ".utils", "calc_recall": ".utils",
           "load_fvecs": ".utils", "load_ivecs": ".utils"}
 
 

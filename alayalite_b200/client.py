@@ -1,9 +1,7 @@
-"""Client: a name -> Index registry with optional on-disk persistence.
+"""Client: a name -> Index / Collection registry with optional on-disk persistence.
 
-Covers the index half of the reference's Client (/root/reference/python/src/alayalite/client.py:31-294):
-create_index / get_index / get_or_create_index / list_indices / delete_index / save_index / reset and
-reload-on-construction. Collections (documents + metadata in pandas) sit above the hot path and are
-out of scope; the reference's Collection works unchanged on top of Index.
+Mirrors the reference's Client (/root/reference/python/src/alayalite/client.py:31-294): create / get /
+get_or_create / list / delete / save for indices and collections, reset, and reload-on-construction.
 """
 
 from __future__ import annotations
@@ -12,8 +10,9 @@ import json
 import os
 import shutil
 
+from .collection import Collection
 from .index import Index
-from .schema import IndexParams, is_index_url
+from .schema import IndexParams, is_collection_url, is_index_url
 
 __all__ = ["Client"]
 
@@ -21,6 +20,7 @@ __all__ = ["Client"]
 class Client:
     def __init__(self, url=None):
         self._indices = {}
+        self._collections = {}
         self._url = None
         if url is None:
             return
@@ -28,8 +28,56 @@ class Client:
         os.makedirs(self._url, exist_ok=True)
         for name in sorted(os.listdir(self._url)):
             folder = os.path.join(self._url, name)
-            if os.path.isdir(folder) and is_index_url(folder):
+            if not os.path.isdir(folder):
+                continue
+            if is_collection_url(folder):
+                self._collections[name] = Collection.load(self._url, name)
+            elif is_index_url(folder):
                 self._indices[name] = Index.load(self._url, name)
+
+    def _free_name(self, name):
+        if name in self._indices or name in self._collections:
+            raise RuntimeError(f"A collection or index with name '{name}' already exists")
+
+    def _save(self, registry, kind, name):
+        self._need_url("Client is not initialized with a url")
+        if name not in registry:
+            raise RuntimeError(f"{kind} '{name}' does not exist")
+        folder = os.path.join(self._url, name)
+        schema = registry[name].save(folder)
+        with open(os.path.join(folder, "schema.json"), "w", encoding="utf-8") as f:
+            json.dump(schema, f, indent=4)
+
+    def _delete(self, registry, kind, name, delete_on_disk):
+        if name not in registry:
+            raise RuntimeError(f"{kind} '{name}' does not exist")
+        del registry[name]
+        if delete_on_disk:
+            self._need_url()
+            shutil.rmtree(os.path.join(self._url, name), ignore_errors=True)
+
+    # -- collections ------------------------------------------------------------------------------
+    def list_collections(self):
+        return list(self._collections)
+
+    def get_collection(self, name: str = "default"):
+        return self._collections.get(name)
+
+    def create_collection(self, name: str = "default", **kwargs) -> Collection:
+        self._free_name(name)
+        self._collections[name] = Collection(name, IndexParams.from_kwargs(**kwargs))
+        return self._collections[name]
+
+    def get_or_create_collection(self, name: str, **kwargs) -> Collection:
+        return self._collections[name] if name in self._collections else self.create_collection(name, **kwargs)
+
+    def delete_collection(self, collection_name: str, delete_on_disk: bool = False):
+        self._delete(self._collections, "Collection", collection_name, delete_on_disk)
+
+    def save_collection(self, collection_name: str):
+        self._save(self._collections, "Collection", collection_name)
+
+    # -- indices ----------------------------------------------------------------------------------
 
     def list_indices(self):
         return list(self._indices)
@@ -38,8 +86,7 @@ class Client:
         return self._indices.get(name)
 
     def create_index(self, name: str = "default", **kwargs) -> Index:
-        if name in self._indices:
-            raise RuntimeError(f"A collection or index with name '{name}' already exists")
+        self._free_name(name)
         self._indices[name] = Index(name, IndexParams.from_kwargs(**kwargs))
         return self._indices[name]
 
@@ -51,25 +98,15 @@ class Client:
             raise RuntimeError(message)
 
     def delete_index(self, index_name: str, delete_on_disk: bool = False):
-        if index_name not in self._indices:
-            raise RuntimeError(f"Index '{index_name}' does not exist")
-        del self._indices[index_name]
-        if delete_on_disk:
-            self._need_url()
-            shutil.rmtree(os.path.join(self._url, index_name), ignore_errors=True)
+        self._delete(self._indices, "Index", index_name, delete_on_disk)
 
     def save_index(self, index_name: str):
-        self._need_url("Client is not initialized with a url")
-        if index_name not in self._indices:
-            raise RuntimeError(f"Index '{index_name}' does not exist")
-        folder = os.path.join(self._url, index_name)
-        schema = self._indices[index_name].save(folder)
-        with open(os.path.join(folder, "schema.json"), "w", encoding="utf-8") as f:
-            json.dump(schema, f, indent=4)
+        self._save(self._indices, "Index", index_name)
 
     def reset(self, delete_on_disk: bool = False):
         if delete_on_disk:
             self._need_url()
-            for name in self._indices:
+            for name in list(self._indices) + list(self._collections):
                 shutil.rmtree(os.path.join(self._url, name), ignore_errors=True)
         self._indices = {}
+        self._collections = {}
