@@ -180,7 +180,18 @@ struct U64x2 {
 };
 __device__ __forceinline__ U64x2 ldg128_pairs(const void *p) {
   U64x2 r;
+#ifndef AB_LOADMODE
+#define AB_LOADMODE 0
+#endif
+#if AB_LOADMODE == 0
   asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+#elif AB_LOADMODE == 1
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+#elif AB_LOADMODE == 2
+  asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+#else
+  asm volatile("ld.global.nc.L1::evict_first.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
+#endif
   return r;
 }
 __device__ __forceinline__ unsigned long long f2sub(unsigned long long x, unsigned long long y) {
@@ -277,6 +288,66 @@ __device__ __forceinline__ float raw_distance1(const uint8_t *r0, const U64x2 (&
 #pragma unroll
   for (int o = TPV / 2; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
   return IP ? -s0 : s0;
+}
+
+// Up to three candidates per group in flight with the query chunks read from shared memory *after* the
+// row loads have been issued: no registers are pinned by the query while the loads are outstanding, so
+// a lane can keep 3 * CPL 128-bit loads in flight inside the same register budget (12 at d = 128).
+// Returns candidate c's distance in the lanes with (lg % P) == c, P = 1 / 2 / 4 for NC = 1 / 2 / 3.
+template <bool IP, int TPV, int CPL, bool EXACT, int NC>
+__device__ __forceinline__ float raw_distance_multi(const uint8_t *r0, const uint8_t *r1, const uint8_t *r2,
+                                                    const float *q_smem, int nchunks, int lg) {
+  static_assert(NC >= 1 && NC <= 3 && TPV >= 4, "");
+  U64x2 x0[CPL], x1[NC > 1 ? CPL : 1], x2[NC > 2 ? CPL : 1];
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    if (EXACT || lg + i * TPV < nchunks) {
+      x0[i] = ldg128_pairs(r0 + i * TPV * 16);
+      if (NC > 1) x1[i] = ldg128_pairs(r1 + i * TPV * 16);
+      if (NC > 2) x2[i] = ldg128_pairs(r2 + i * TPV * 16);
+    } else {
+      x0[i].a = x0[i].b = 0ull;
+      if (NC > 1) x1[i].a = x1[i].b = 0ull;
+      if (NC > 2) x2[i].a = x2[i].b = 0ull;
+    }
+  }
+  __syncwarp();  // scheduling fence: every load is issued before the first shared-memory read / FMA
+  unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull;
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    U64x2 q;
+    q.a = q.b = 0ull;
+    if (EXACT || lg + i * TPV < nchunks) {
+      const ulonglong2 t = reinterpret_cast<const ulonglong2 *>(q_smem)[lg + i * TPV];
+      q.a = t.x;
+      q.b = t.y;
+    }
+    a0 = raw_pairs_term<IP>(q, x0[i], a0);
+    if (NC > 1) a1 = raw_pairs_term<IP>(q, x1[i], a1);
+    if (NC > 2) a2 = raw_pairs_term<IP>(q, x2[i], a2);
+  }
+  float s = f2sum(a0);
+  int first = 1;  // first butterfly offset still to do
+  if (NC == 2) {
+    const float s1 = f2sum(a1);
+    const bool b0 = lg & 1;
+    s = (b0 ? s1 : s) + __shfl_xor_sync(0xFFFFFFFFu, b0 ? s : s1, 1);
+    first = 2;
+  } else if (NC == 3) {
+    const float s1 = f2sum(a1), s2 = f2sum(a2);
+    const bool b0 = lg & 1, b1 = lg & 2;
+    // xor 1: even lanes keep candidates {0, 2}, odd lanes {1, pad}
+    const float t0 = (b0 ? s1 : s) + __shfl_xor_sync(0xFFFFFFFFu, b0 ? s : s1, 1);
+    const float t1 = (b0 ? 0.f : s2) + __shfl_xor_sync(0xFFFFFFFFu, b0 ? s2 : 0.f, 1);
+    // xor 2: lanes with bit 1 clear keep the first of their pair, the others the second
+    s = (b1 ? t1 : t0) + __shfl_xor_sync(0xFFFFFFFFu, b1 ? t0 : t1, 2);
+    first = 4;
+  }
+#pragma unroll
+  for (int o = TPV / 2; o >= 1; o >>= 1) {
+    if (o >= first) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  }
+  return IP ? -s : s;
 }
 
 // ---- quantizer (include/space/quant/sq8.hpp:120-132, sq4.hpp:120-132) --------------------------

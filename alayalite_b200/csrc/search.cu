@@ -23,6 +23,7 @@
 // Distances are plain fp32; given equal distance values the traversal is step-for-step the
 // reference's, so ids are identical up to fp32 summation-order effects.
 #include <cfloat>
+#include <cstdlib>
 
 #include "distance.cuh"
 #include "search.cuh"
@@ -50,15 +51,16 @@ struct Visited {
   bool spilled;
 };
 
-__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int shift) { return (key * 0x9E3779B1u) >> shift; }
+// multiply-shift range reduction: any table size, no power-of-two rounding of the shared-memory footprint
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t size) { return __umulhi(key * 0x9E3779B1u, size); }
 
 // Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
 // The probe loop is driven by a warp vote, so the warp stays converged (a per-lane probe loop leaves the
 // lanes split under independent thread scheduling, and every later warp-level primitive then takes the
 // compiler's slow divergent path).
 __device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, uint32_t key, bool active) {
-  const uint32_t hmask = a.hash_size - 1;
-  uint32_t slot = hash_slot(key, a.hash_shift);
+  const uint32_t hsize = a.hash_size;
+  uint32_t slot = hash_slot(key, hsize);
   bool is_new = false;
   bool pending = active;
   if (!vs.spilled) {
@@ -67,7 +69,7 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, ui
         const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
         is_new = old == kEmptyId;
         pending = !(is_new || old == key);
-        slot = (slot + 1) & hmask;
+        slot = slot + 1 == hsize ? 0u : slot + 1;
       }
     }
     return is_new;
@@ -79,7 +81,7 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, ui
       const uint32_t cur = vs.hash[slot];
       absent = cur == kEmptyId;
       pending = !(absent || cur == key);
-      slot = (slot + 1) & hmask;
+      slot = slot + 1 == hsize ? 0u : slot + 1;
     }
   }
   if (absent) {
@@ -98,25 +100,42 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, ui
 // before it.
 __device__ __forceinline__ void pool_insert(uint2 *pool, int &size, int &cur, int ef, float d, uint32_t v, int lane,
                                             bool expanded = false) {
-  int pos = 0;  // upper bound: number of entries with dist <= d
-  for (int base = 0; base < size; base += 32) {
-    const int i = base + lane;
-    const uint32_t b = __ballot_sync(kFull, i < size && __uint_as_float(pool[i].x) <= d);
-    pos += __popc(b);
-    if (b != kFull) break;
-  }
+  int pos;  // upper bound: number of entries with dist <= d
   const int nsize = min(size + 1, ef);
-  for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 > pos; base -= 32) {
-    const int i = base + lane;
-    const bool mv = i > pos && i < nsize;
-    uint2 t = make_uint2(0u, 0u);
-    if (mv) t = pool[i - 1];
+  if (ef <= 64) {
+    // the pool fits two entries per lane: read everything first, then every entry behind the insert
+    // position moves one slot to the right in a single step
+    const int i1 = lane + 32;
+    const uint2 e0 = pool[lane];
+    uint2 e1 = make_uint2(0u, 0u);
+    if (size > 32 && i1 < size) e1 = pool[i1];
+    pos = __popc(__ballot_sync(kFull, lane < size && __uint_as_float(e0.x) <= d));
+    if (size > 32) pos += __popc(__ballot_sync(kFull, i1 < size && __uint_as_float(e1.x) <= d));
     __syncwarp();
-    if (mv) pool[i] = t;
+    if (lane >= pos && lane < size && lane + 1 < nsize) pool[lane + 1] = e0;
+    if (size > 32 && i1 >= pos && i1 < size && i1 + 1 < nsize) pool[i1 + 1] = e1;
+    if (lane == 0) pool[pos] = make_uint2(__float_as_uint(d), v);
+    __syncwarp();
+  } else {
+    pos = 0;
+    for (int base = 0; base < size; base += 32) {
+      const int i = base + lane;
+      const uint32_t b = __ballot_sync(kFull, i < size && __uint_as_float(pool[i].x) <= d);
+      pos += __popc(b);
+      if (b != kFull) break;
+    }
+    for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 > pos; base -= 32) {
+      const int i = base + lane;
+      const bool mv = i > pos && i < nsize;
+      uint2 t = make_uint2(0u, 0u);
+      if (mv) t = pool[i - 1];
+      __syncwarp();
+      if (mv) pool[i] = t;
+      __syncwarp();
+    }
+    if (lane == 0) pool[pos] = make_uint2(__float_as_uint(d), v);
     __syncwarp();
   }
-  if (lane == 0) pool[pos] = make_uint2(__float_as_uint(d), v);
-  __syncwarp();
   size = nsize;
   if (expanded) {
     if (pos <= cur) cur = min(cur + 1, nsize);
@@ -194,13 +213,61 @@ __device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpS
   return out;
 }
 
+// Raw-space fast path, three candidates per group in flight, query read from shared memory
+// (distance.cuh raw_distance_multi). Used when a row is at most 4 chunks per lane.
+#ifndef AB_HASH_FACTOR
+#define AB_HASH_FACTOR 1.34f
+#endif
+#ifndef AB_INFLIGHT
+#define AB_INFLIGHT 3
+#endif
+#ifndef AB_MINBLOCKS
+#define AB_MINBLOCKS 3
+#endif
+template <bool IP, int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ float eval_lanes_raw3(const SearchArgs &a, const WarpSmem &ws, uint32_t v, bool want, int lane) {
+  constexpr int G = 32 / TPV;
+  const uint32_t mask = __ballot_sync(kFull, want);
+  const int cnt = __popc(mask);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  if (want) ws.cand[rank] = v;
+  __syncwarp();
+  const int g = lane / TPV, lg = lane % TPV;
+  const uint8_t *lane_base = a.rows + lg * 16;
+  for (int base = 0; base < cnt; base += AB_INFLIGHT * G) {
+    const int rem = cnt - base;  // warp-uniform
+    const int k0 = base + g, k1 = k0 + G, k2 = k1 + G;
+    const uint8_t *r0 = lane_base + size_t(ws.cand[k0 < cnt ? k0 : 0]) * a.row_stride;
+    if (AB_INFLIGHT > 2 && rem > 2 * G) {
+      const uint8_t *r1 = lane_base + size_t(ws.cand[k1 < cnt ? k1 : 0]) * a.row_stride;
+      const uint8_t *r2 = lane_base + size_t(ws.cand[k2 < cnt ? k2 : 0]) * a.row_stride;
+      const float d = raw_distance_multi<IP, TPV, CPL, EXACT, 3>(r0, r1, r2, ws.q_raw, a.nchunks, lg);
+      const int k = k0 + lg * G;  // lanes 0..2 of the group hold candidates 0..2
+      if (lg < 3 && k < cnt) ws.cdist[k] = d;
+    } else if (rem > G) {
+      const uint8_t *r1 = lane_base + size_t(ws.cand[k1 < cnt ? k1 : 0]) * a.row_stride;
+      const float d = raw_distance_multi<IP, TPV, CPL, EXACT, 2>(r0, r1, r1, ws.q_raw, a.nchunks, lg);
+      const int k = k0 + lg * G;
+      if (lg < 2 && k < cnt) ws.cdist[k] = d;
+    } else {
+      const float d = raw_distance_multi<IP, TPV, CPL, EXACT, 1>(r0, r0, r0, ws.q_raw, a.nchunks, lg);
+      if (lg == 0 && k0 < cnt) ws.cdist[k0] = d;
+    }
+  }
+  __syncwarp();
+  const float out = want ? ws.cdist[rank] : FLT_MAX;
+  __syncwarp();
+  return out;
+}
+
 // CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
 // CPL == 0 is the generic path for any space.
 template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
-__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? 3 : 1) beam_search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? AB_MINBLOCKS : 2) beam_search_kernel(const SearchArgs a) {
   constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
   constexpr int MAXC = 8;
-  constexpr int QREGS = FAST ? CPL : 1;
+  constexpr bool FAST3 = FAST && CPL <= 4;  // three candidates in flight, query from shared memory
+  constexpr int QREGS = (FAST && !FAST3) ? CPL : 1;
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = lane_id();
   // redux lands in a uniform register: the compiler then knows every per-warp address below is warp-uniform
@@ -298,13 +365,15 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
     uint32_t u = a.ep;
     U64x2 qreg[QREGS];
-    if (FAST) load_query_regs<TPV, QREGS, EXACT>(ws.q_raw, a.nchunks, lane % TPV, qreg);
+    if (FAST && !FAST3) load_query_regs<TPV, QREGS, EXACT>(ws.q_raw, a.nchunks, lane % TPV, qreg);
     // distance of the candidate in every lane with WANT; afterwards ws.cand / ws.cdist hold the wanted ids and
     // distances compacted in lane order. Warp-uniform values are re-read from there (uniform shared-memory
     // loads) rather than shuffled, which keeps the control flow provably convergent for the compiler.
     auto eval = [&](uint32_t id, bool want) -> float {
       float dd;
-      if (FAST) {
+      if constexpr (FAST3) {
+        dd = eval_lanes_raw3<IP, TPV, CPL, EXACT>(a, ws, id, want, lane);
+      } else if constexpr (FAST) {
         dd = eval_lanes_raw<IP, TPV, QREGS, EXACT>(a, ws, qreg, id, want, lane);
       } else {
         dd = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, id, want, lane);
@@ -558,6 +627,11 @@ template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
 void launch_one(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
   auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT>;
   AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes)));
+  // The unified L1 / shared-memory array also stages the row loads in flight: ask for exactly the shared memory
+  // the resident CTAs need and leave the rest to L1.
+  const size_t need = size_t(p.ctas_per_sm) * (p.smem_bytes + 1024);
+  const int pct = static_cast<int>(std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024)));
+  AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   kern<<<dim3(p.ctas), dim3(p.warps_per_cta * 32), p.smem_bytes, s>>>(a);
 }
 
@@ -607,40 +681,47 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
                        size_t smem_limit) {
   SearchPlan p{};
   p.tpv = pick_tpv(nchunks);
-  // size the hash so that the average query stays below the 3/4 spill mark: visited ids per query grow like
-  // ratio * ef, ratio ~ 21-24 on SIFT-like graphs and higher on harder data (taken from earlier searches)
+  // Hash entries per warp so that the average query stays below the 3/4 spill mark: visited ids per query grow
+  // like ratio * ef, ratio ~ 21-24 on SIFT-like graphs and higher on harder data (taken from earlier searches).
   const float ratio = std::max(24.0f, visit_ratio);
-  const uint32_t target = static_cast<uint32_t>(ratio * 1.34f * static_cast<float>(ef));
-  uint32_t h = 512;
-  while (h < target && h < 16384u) h <<= 1;
+  static const float hash_factor = getenv("AB_HASH_FACTOR") ? static_cast<float>(atof(getenv("AB_HASH_FACTOR"))) : AB_HASH_FACTOR;
+  static const int max_warps = getenv("AB_MAX_WARPS") ? atoi(getenv("AB_MAX_WARPS")) : 64;
+  uint32_t h = static_cast<uint32_t>(ratio * hash_factor * static_cast<float>(ef));
+  h = std::min(16384u, std::max(512u, (h + 63u) & ~63u));
   const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;
   const size_t pool_bytes = round_up16(size_t(ef + 1) * 8);
-  auto per_warp = [&](uint32_t hs) { return 256 + size_t(nchunks) * 16 + pool_bytes + size_t(hs) * 4; };
-  // keep at least ~16 resident warps per SM: shrink the hash (queries then spill to the bitmap) if needed
-  // prefer a hash that holds the whole visited set (~22 * ef ids) as long as 12 warps still fit per SM;
-  // below that, shrink it and let long queries continue in their global bitmap
-  while (h > 512 && (smem_limit - 2 * cta_fixed) / per_warp(h) < 12) h >>= 1;
+  const size_t other = 256 + size_t(nchunks) * 16 + pool_bytes;
+  // keep at least 12 resident warps per SM: below that, shrink the hash and let long queries continue in
+  // their global bitmap
+  const size_t budget12 = (smem_limit - cta_fixed - 1024) / 12;
+  if (other + size_t(h) * 4 > budget12 && budget12 > other + 512 * 4) h = static_cast<uint32_t>((budget12 - other) / 4) & ~63u;
+  h = std::max(512u, h);
   p.hash_size = h;
-  const size_t pw = per_warp(h);
-  int warps_per_sm = static_cast<int>((smem_limit - 2 * cta_fixed - 2048) / pw);
-  warps_per_sm = std::max(1, std::min(warps_per_sm, 32));
-  // CTAs of up to 8 warps; as many CTAs per SM as fit
-  int wpc = std::min(8, warps_per_sm);
-  int ctas_per_sm = std::max(1, warps_per_sm / wpc);
-  while (ctas_per_sm * (cta_fixed + size_t(wpc) * pw + 1024) > smem_limit && ctas_per_sm > 1) ctas_per_sm--;
-  p.warps_per_cta = wpc;
-  p.smem_bytes = cta_fixed + size_t(wpc) * pw;
-  const int want_ctas = static_cast<int>((nq + wpc - 1) / wpc);
-  p.ctas = std::max(1, std::min(want_ctas, sm_count * ctas_per_sm));
+  const size_t pw = other + size_t(h) * 4;
+  // resident warps the register file allows: the three-in-flight raw kernels are built for 3 x 256 threads,
+  // everything else (SQ spaces, rows above 128 chunks) for 2 x 256
+  const int reg_warps = (quant == AB_QUANT_NONE && nchunks <= 128) ? 8 * AB_MINBLOCKS : 16;
+  // CTA size: whatever packs the most warps into the SM (each CTA also pays cta_fixed + 1 KB of reserved smem)
+  int best_wpc = 1, best_ctas = 1;
+  for (int wpc = 8; wpc >= 1; --wpc) {
+    const int by_smem = static_cast<int>(smem_limit / (cta_fixed + size_t(wpc) * pw + 1024));
+    const int ctas = std::min(by_smem, std::min(reg_warps, max_warps) / wpc);
+    if (ctas * wpc > best_ctas * best_wpc) {
+      best_wpc = wpc;
+      best_ctas = ctas;
+    }
+  }
+  p.warps_per_cta = best_wpc;
+  p.smem_bytes = cta_fixed + size_t(best_wpc) * pw;
+  p.ctas_per_sm = best_ctas;
+  const int want_ctas = static_cast<int>((nq + best_wpc - 1) / best_wpc);
+  p.ctas = std::max(1, std::min(want_ctas, sm_count * best_ctas));
   p.slots = p.ctas * p.warps_per_cta;
   return p;
 }
 
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args_in, cudaStream_t stream) {
   SearchArgs args = args_in;
-  int lg = 0;
-  while ((1u << lg) < args.hash_size) lg++;
-  args.hash_shift = 32 - lg;
   args.hash_limit = args.hash_size - args.hash_size / 4;
   const bool ip = args.metric != AB_METRIC_L2;
   if (quant == AB_QUANT_NONE) {

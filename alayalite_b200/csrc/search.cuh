@@ -38,9 +38,8 @@ struct SearchArgs {
   uint32_t *pool_sizes;
   // scheduling + visited set
   uint32_t *work_counter;       // zeroed before launch
-  uint32_t hash_size;           // shared-memory hash entries per warp (power of two)
-  int hash_shift;               // 32 - log2(hash_size)      } filled in by launch_search
-  uint32_t hash_limit;          // spill to the bitmap past this many ids (3/4 load)
+  uint32_t hash_size;           // shared-memory hash entries per warp (multiple of 64)
+  uint32_t hash_limit;          // spill to the bitmap past this many ids (3/4 load); filled in by launch_search
   uint32_t *bitmaps;            // [slots, bitmap_words] all zero between launches
   size_t bitmap_words;
   unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, spilled queries}
@@ -65,6 +64,7 @@ struct SearchPlan {
   int tpv;            // lanes per candidate row
   int warps_per_cta;
   int ctas;
+  int ctas_per_sm;    // resident CTAs per SM the plan counts on
   uint32_t hash_size;
   size_t smem_bytes;
   int slots;          // ctas * warps_per_cta (bitmap slots needed)
