@@ -165,8 +165,8 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   if (nq == 0) return;
   const int quant = ix->params.quantization_type;
   const int nchunks = quant == AB_QUANT_NONE ? ix->raw_chunks : ix->code_chunks;
-  SearchPlan plan = plan_search(quant, nchunks, ix->table_len, ix->visit_ratio, ef, static_cast<uint32_t>(nq), ix->sm_count,
-                                ix->smem_limit);
+  SearchPlan plan = plan_search(quant, nchunks, ix->table_len, ix->visit_ratio, ef, static_cast<uint32_t>(nq),
+                                static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
   // private visited bitmaps, one per resident warp, all-zero between launches
   const size_t words = round_up((std::max<uint64_t>(ix->capacity, ix->n) + 31) / 32, 4);
   if (ix->bitmap_words != words || ix->bitmap_slots < plan.slots) {

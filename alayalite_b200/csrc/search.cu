@@ -44,53 +44,90 @@ struct WarpSmem {
   float *cdist;       // [32] their distances
 };
 
-// Visited set of one query. Derived values (mask, shift, the warp's bitmap) are recomputed from the
+// Visited set of one query. Derived values (the warp's bitmap, table parameters) are recomputed from the
 // kernel arguments where needed instead of living in registers across the hot loop.
 struct Visited {
   uint32_t *hash;
-  bool spilled;
+  bool spilled;      // the hash is frozen, new ids go to the bitmap
+  bool bitmap_used;  // the warp's global bitmap holds bits and must be cleared after the query
 };
 
 // multiply-shift range reduction: any table size, no power-of-two rounding of the shared-memory footprint
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t size) { return __umulhi(key * 0x9E3779B1u, size); }
 
+__device__ __forceinline__ bool bitmap_test_and_set(const SearchArgs &a, uint32_t key) {
+  uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
+  const uint32_t bit = 1u << (key & 31);
+  return (atomicOr(&bitmap[key >> 5], bit) & bit) == 0;
+}
+
 // Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
 // The probe loop is driven by a warp vote, so the warp stays converged (a per-lane probe loop leaves the
 // lanes split under independent thread scheduling, and every later warp-level primitive then takes the
 // compiler's slow divergent path).
-__device__ __forceinline__ bool visit(const SearchArgs &a, const Visited &vs, uint32_t key, bool active) {
+//
+// Two table formats, both exact (never a false "visited", never a false "new"):
+//  * 32-bit entries holding the id itself;
+//  * 16-bit entries (a.hash_rbits > 0) when the id range is small enough relative to the table: the id is
+//    scrambled by a bijection of the b-bit id space (odd multiplier mod 2^b), the table slot is the scaled
+//    scramble, and the entry keeps what the slot does not already say -- the position inside the slot's
+//    bucket of the id space (r, rbits bits) and the displacement from the home slot (linear probing). An
+//    entry equal to (displacement, r) at slot home + displacement can only belong to this id. Half the
+//    shared memory per warp, which matters twice: more resident warps, and more of the unified L1/shared
+//    array left to stage loads in flight. A probe that runs out of displacement range falls through to
+//    the warp's bitmap (exact, rare).
+__device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t key, bool active) {
   const uint32_t hsize = a.hash_size;
-  uint32_t slot = hash_slot(key, hsize);
   bool is_new = false;
   bool pending = active;
-  if (!vs.spilled) {
+  bool to_bitmap = false;
+  if (a.hash_rbits != 0) {
+    const uint32_t x = (key * 0x9E3779B1u) << a.hash_xshift;
+    uint32_t slot = __umulhi(x, hsize);
+    uint32_t code = __umulhi(x * hsize, a.hash_rmul);  // displacement 0
+    const uint32_t dstep = 1u << a.hash_rbits;
+    unsigned short *h16 = reinterpret_cast<unsigned short *>(vs.hash);
     while (__any_sync(kFull, pending)) {
       if (pending) {
-        const uint32_t old = atomicCAS(&vs.hash[slot], kEmptyId, key);
-        is_new = old == kEmptyId;
-        pending = !(is_new || old == key);
+        uint32_t old;
+        if (!vs.spilled) {
+          old = atomicCAS(&h16[slot], static_cast<unsigned short>(0xFFFFu), static_cast<unsigned short>(code));
+          is_new = old == 0xFFFFu;
+        } else {
+          old = h16[slot];
+          to_bitmap = old == 0xFFFFu;
+        }
+        pending = !(old == 0xFFFFu || old == code);
+        slot = slot + 1 == hsize ? 0u : slot + 1;
+        code += dstep;
+        if (pending && code >= a.hash_dlimit) {  // out of displacement range
+          pending = false;
+          to_bitmap = true;
+        }
+      }
+    }
+  } else {
+    uint32_t slot = hash_slot(key, hsize);
+    while (__any_sync(kFull, pending)) {
+      if (pending) {
+        uint32_t old;
+        if (!vs.spilled) {
+          old = atomicCAS(&vs.hash[slot], kEmptyId, key);
+          is_new = old == kEmptyId;
+        } else {
+          old = vs.hash[slot];
+          to_bitmap = old == kEmptyId;
+        }
+        pending = !(old == kEmptyId || old == key);
         slot = slot + 1 == hsize ? 0u : slot + 1;
       }
     }
-    return is_new;
   }
-  // spilled: the hash is frozen (read-only), new ids go to the warp's bitmap in global memory
-  bool absent = false;
-  while (__any_sync(kFull, pending)) {
-    if (pending) {
-      const uint32_t cur = vs.hash[slot];
-      absent = cur == kEmptyId;
-      pending = !(absent || cur == key);
-      slot = slot + 1 == hsize ? 0u : slot + 1;
-    }
+  if (__any_sync(kFull, to_bitmap)) {
+    if (to_bitmap) is_new = bitmap_test_and_set(a, key);
+    vs.bitmap_used = true;
+    __syncwarp();
   }
-  if (absent) {
-    uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
-    const uint32_t bit = 1u << (key & 31);
-    const uint32_t old = atomicOr(&bitmap[key >> 5], bit);
-    is_new = (old & bit) == 0;
-  }
-  __syncwarp();
   return is_new;
 }
 
@@ -280,7 +317,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
   size_t off = (QUANT != AB_QUANT_NONE ? size_t(a.table_len) * 8 : 0);
   const size_t q_bytes = size_t(a.nchunks) * 16;
   const size_t pool_bytes = round_up16(size_t(a.ef + 1) * 8);
-  const size_t per_warp = 256 + q_bytes + pool_bytes + size_t(a.hash_size) * 4;
+  const size_t per_warp = 256 + q_bytes + pool_bytes + size_t(a.hash_words) * 4;
   uint8_t *wbase = smem + off + size_t(warp) * per_warp;
   WarpSmem ws;
   ws.cand = reinterpret_cast<uint32_t *>(wbase);
@@ -351,7 +388,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
         ws.q_code[j] = static_cast<uint8_t>((first << 4) | second);
       }
     }
-    for (uint32_t i = lane; i < a.hash_size / 4; i += 32) reinterpret_cast<uint4 *>(ws.hash)[i] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
+    for (uint32_t i = lane; i < a.hash_words / 4; i += 32) reinterpret_cast<uint4 *>(ws.hash)[i] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
     for (int i = lane; i <= ef; i += 32) {
       ws.pool[i] = make_uint2(0u, 0u);
     }
@@ -361,6 +398,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     uint32_t nvis = 0;
     uint32_t ndc = 0, hops = 0, ndc_ov = 0;  // per query: far below 2^32
     vs.spilled = false;
+    vs.bitmap_used = false;
 
     // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
     uint32_t u = a.ep;
@@ -520,7 +558,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       }
       if (lane == 0) a.pool_sizes[qi] = size;
     }
-    if (vs.spilled) {
+    if (vs.bitmap_used) {
       // give the private bitmap back all-zero (the reference allocates + zeroes one per query)
       uint4 *bm = reinterpret_cast<uint4 *>(a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words);
       for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
@@ -528,7 +566,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     if (lane == 0) {
       atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
       atomicAdd(&a.stats[1], static_cast<unsigned long long>(hops));
-      if (vs.spilled) atomicAdd(&a.stats[3], 1ull);
+      if (vs.bitmap_used) atomicAdd(&a.stats[3], 1ull);
     }
     __syncwarp();
   }
@@ -677,40 +715,79 @@ void launch_search_t(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
 
 }  // namespace
 
-SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, int sm_count,
-                       size_t smem_limit) {
+SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
+                       int sm_count, size_t smem_limit) {
   SearchPlan p{};
   p.tpv = pick_tpv(nchunks);
-  // Hash entries per warp so that the average query stays below the 3/4 spill mark: visited ids per query grow
-  // like ratio * ef, ratio ~ 21-24 on SIFT-like graphs and higher on harder data (taken from earlier searches).
-  const float ratio = std::max(24.0f, visit_ratio);
-  static const float hash_factor = getenv("AB_HASH_FACTOR") ? static_cast<float>(atof(getenv("AB_HASH_FACTOR"))) : AB_HASH_FACTOR;
+  static const float hash_factor = getenv("AB_HASH_FACTOR") ? static_cast<float>(atof(getenv("AB_HASH_FACTOR"))) : 1.7f;
   static const int max_warps = getenv("AB_MAX_WARPS") ? atoi(getenv("AB_MAX_WARPS")) : 64;
+  static const int hash16 = getenv("AB_HASH16") ? atoi(getenv("AB_HASH16")) : 1;
+  // Hash entries per warp so that nearly every query stays below the 3/4 spill mark: visited ids per query
+  // grow like ratio * ef, ratio ~ 21-24 on SIFT-like graphs and higher on harder data (taken from earlier
+  // searches of this index); 1.7 = 1 / 0.75 load x 1.28 for the spread between queries.
+  const float ratio = std::max(24.0f, visit_ratio);
   uint32_t h = static_cast<uint32_t>(ratio * hash_factor * static_cast<float>(ef));
-  h = std::min(16384u, std::max(512u, (h + 63u) & ~63u));
+  h = std::min(32768u, std::max(512u, (h + 63u) & ~63u));
   const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;
   const size_t pool_bytes = round_up16(size_t(ef + 1) * 8);
   const size_t other = 256 + size_t(nchunks) * 16 + pool_bytes;
+
+  // 16-bit entries if the id range is small enough for (displacement, remainder) to fit (see visit())
+  int idbits = 1;
+  while (idbits < 31 && (1ull << idbits) < n_rows) idbits++;
+  auto quotient = [&](uint32_t entries, SearchPlan &q) {
+    q.hash_rbits = 0;
+    if (!hash16 || entries >= (1ull << idbits)) return false;
+    const uint64_t S = uint64_t(entries) << (32 - idbits);  // scaled scramble units per table slot
+    const uint32_t M = static_cast<uint32_t>((1ull << 32) / S) + 1;
+    int rbits = 1;
+    while ((1u << rbits) < M) rbits++;
+    if (rbits > 11) return false;  // fewer than 5 displacement bits: keep 32-bit entries
+    q.hash_rbits = rbits;
+    q.hash_xshift = 32 - idbits;
+    q.hash_rmul = M;
+    q.hash_dlimit = ((1u << (16 - rbits)) - 1) << rbits;
+    return true;
+  };
+  uint32_t entry_bytes = 4;
+  if (quotient(std::max(h, 2048u), p)) {  // 16-bit entries are cheap: never below 2048 of them (4 KB)
+    h = std::max(h, 2048u);
+    entry_bytes = 2;
+  }
   // keep at least 12 resident warps per SM: below that, shrink the hash and let long queries continue in
   // their global bitmap
   const size_t budget12 = (smem_limit - cta_fixed - 1024) / 12;
-  if (other + size_t(h) * 4 > budget12 && budget12 > other + 512 * 4) h = static_cast<uint32_t>((budget12 - other) / 4) & ~63u;
-  h = std::max(512u, h);
+  if (other + size_t(h) * entry_bytes > budget12 && budget12 > other + 512 * 4) {
+    h = std::max(512u, static_cast<uint32_t>((budget12 - other) / entry_bytes) & ~63u);
+    entry_bytes = quotient(h, p) ? 2 : 4;
+  }
   p.hash_size = h;
-  const size_t pw = other + size_t(h) * 4;
+  p.hash_words = h * entry_bytes / 4;
+  const size_t pw = other + size_t(p.hash_words) * 4;
   // resident warps the register file allows: the three-in-flight raw kernels are built for 3 x 256 threads,
   // everything else (SQ spaces, rows above 128 chunks) for 2 x 256
-  const int reg_warps = (quant == AB_QUANT_NONE && nchunks <= 128) ? 8 * AB_MINBLOCKS : 16;
-  // CTA size: whatever packs the most warps into the SM (each CTA also pays cta_fixed + 1 KB of reserved smem)
-  int best_wpc = 1, best_ctas = 1;
-  for (int wpc = 8; wpc >= 1; --wpc) {
-    const int by_smem = static_cast<int>(smem_limit / (cta_fixed + size_t(wpc) * pw + 1024));
-    const int ctas = std::min(by_smem, std::min(reg_warps, max_warps) / wpc);
-    if (ctas * wpc > best_ctas * best_wpc) {
-      best_wpc = wpc;
-      best_ctas = ctas;
+  const int reg_warps = std::min(max_warps, (quant == AB_QUANT_NONE && nchunks <= 128) ? 8 * AB_MINBLOCKS : 16);
+  // CTA size: whatever packs the most warps into the SM (each CTA also pays cta_fixed + 1 KB of reserved
+  // shared memory). The unified L1 / shared-memory array also stages the row loads in flight, and the step
+  // from a 196 KB to a 228 KB carve-out halves what is left for that (60 -> 28 KB): stay at or below 196 KB
+  // unless that costs more than a fifth of the resident warps.
+  auto pack = [&](size_t limit, int &wpc_out, int &ctas_out) {
+    wpc_out = 1;
+    ctas_out = 0;
+    for (int wpc = 8; wpc >= 1; --wpc) {
+      const int by_smem = static_cast<int>(limit / (cta_fixed + size_t(wpc) * pw + 1024));
+      const int ctas = std::min(by_smem, reg_warps / wpc);
+      if (ctas * wpc > ctas_out * wpc_out) {
+        wpc_out = wpc;
+        ctas_out = ctas;
+      }
     }
-  }
+  };
+  int wpc_a, ctas_a, wpc_b, ctas_b;
+  pack(std::min(smem_limit, size_t(196) * 1024), wpc_a, ctas_a);
+  pack(smem_limit, wpc_b, ctas_b);
+  const bool small = ctas_a > 0 && 5 * wpc_a * ctas_a >= 4 * wpc_b * ctas_b;
+  const int best_wpc = small ? wpc_a : wpc_b, best_ctas = std::max(1, small ? ctas_a : ctas_b);
   p.warps_per_cta = best_wpc;
   p.smem_bytes = cta_fixed + size_t(best_wpc) * pw;
   p.ctas_per_sm = best_ctas;
@@ -722,7 +799,13 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
 
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args_in, cudaStream_t stream) {
   SearchArgs args = args_in;
-  args.hash_limit = args.hash_size - args.hash_size / 4;
+  args.hash_size = plan.hash_size;
+  args.hash_words = plan.hash_words;
+  args.hash_limit = plan.hash_size - plan.hash_size / 4;
+  args.hash_rbits = plan.hash_rbits;
+  args.hash_xshift = plan.hash_xshift;
+  args.hash_rmul = plan.hash_rmul;
+  args.hash_dlimit = plan.hash_dlimit;
   const bool ip = args.metric != AB_METRIC_L2;
   if (quant == AB_QUANT_NONE) {
     ip ? launch_search_t<AB_QUANT_NONE, true>(plan, args, stream) : launch_search_t<AB_QUANT_NONE, false>(plan, args, stream);

@@ -38,8 +38,14 @@ struct SearchArgs {
   uint32_t *pool_sizes;
   // scheduling + visited set
   uint32_t *work_counter;       // zeroed before launch
-  uint32_t hash_size;           // shared-memory hash entries per warp (multiple of 64)
-  uint32_t hash_limit;          // spill to the bitmap past this many ids (3/4 load); filled in by launch_search
+  // visited-set table, filled in by launch_search from the plan
+  uint32_t hash_size;           // entries per warp (multiple of 64)
+  uint32_t hash_words;          // 32-bit words the table occupies in shared memory
+  uint32_t hash_limit;          // freeze the table and continue in the bitmap past this many ids (3/4 load)
+  int hash_rbits;               // 0: 32-bit entries holding ids; else 16-bit (displacement, remainder) entries
+  int hash_xshift;              // 32 - bits of the id space
+  uint32_t hash_rmul;           // remainder = umulhi(low word of scramble * entries, hash_rmul)
+  uint32_t hash_dlimit;         // first invalid entry code (displacement range exhausted)
   uint32_t *bitmaps;            // [slots, bitmap_words] all zero between launches
   size_t bitmap_words;
   unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, spilled queries}
@@ -65,14 +71,17 @@ struct SearchPlan {
   int warps_per_cta;
   int ctas;
   int ctas_per_sm;    // resident CTAs per SM the plan counts on
-  uint32_t hash_size;
+  uint32_t hash_size;   // visited-table entries per warp
+  uint32_t hash_words;  // 32-bit words of shared memory the table takes
+  int hash_rbits, hash_xshift;
+  uint32_t hash_rmul, hash_dlimit;
   size_t smem_bytes;
   int slots;          // ctas * warps_per_cta (bitmap slots needed)
 };
 
 // visit_ratio: visited ids per query divided by ef, measured on earlier searches of this index (0 = unknown)
-SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, int sm_count,
-                       size_t smem_limit);
+SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
+                       int sm_count, size_t smem_limit);
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
 void launch_rerank(const RerankArgs &args, int sm_count, cudaStream_t stream);
 
