@@ -86,23 +86,35 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
     uint32_t slot = __umulhi(x, hsize);
     uint32_t code = __umulhi(x * hsize, a.hash_rmul);  // displacement 0
     const uint32_t dstep = 1u << a.hash_rbits;
-    unsigned short *h16 = reinterpret_cast<unsigned short *>(vs.hash);
+    // Probe with plain reads; only an empty slot is claimed, with a 32-bit CAS on the word that holds it
+    // (a failed CAS -- the slot or its neighbour half changed meanwhile -- re-reads the same slot).
     while (__any_sync(kFull, pending)) {
       if (pending) {
-        uint32_t old;
-        if (!vs.spilled) {
-          old = atomicCAS(&h16[slot], static_cast<unsigned short>(0xFFFFu), static_cast<unsigned short>(code));
-          is_new = old == 0xFFFFu;
-        } else {
-          old = h16[slot];
-          to_bitmap = old == 0xFFFFu;
-        }
-        pending = !(old == 0xFFFFu || old == code);
-        slot = slot + 1 == hsize ? 0u : slot + 1;
-        code += dstep;
-        if (pending && code >= a.hash_dlimit) {  // out of displacement range
+        const uint32_t sh = (slot & 1u) << 4;
+        const uint32_t w = vs.hash[slot >> 1];
+        const uint32_t cur = (w >> sh) & 0xFFFFu;
+        bool advance = true;
+        if (cur == 0xFFFFu) {
+          if (!vs.spilled) {
+            advance = false;
+            if (atomicCAS(&vs.hash[slot >> 1], w, w ^ ((0xFFFFu ^ code) << sh)) == w) {
+              is_new = true;
+              pending = false;
+            }
+          } else {
+            to_bitmap = true;
+            pending = false;
+          }
+        } else if (cur == code) {
           pending = false;
-          to_bitmap = true;
+        }
+        if (pending && advance) {
+          slot = slot + 1 == hsize ? 0u : slot + 1;
+          code += dstep;
+          if (code >= a.hash_dlimit) {  // out of displacement range
+            pending = false;
+            to_bitmap = true;
+          }
         }
       }
     }
