@@ -766,19 +766,30 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
     h = std::max(h, 2048u);
     entry_bytes = 2;
   }
-  // keep at least 12 resident warps per SM: below that, shrink the hash and let long queries continue in
-  // their global bitmap
-  const size_t budget12 = (smem_limit - cta_fixed - 1024) / 12;
-  if (other + size_t(h) * entry_bytes > budget12 && budget12 > other + 512 * 4) {
-    h = std::max(512u, static_cast<uint32_t>((budget12 - other) / entry_bytes) & ~63u);
-    entry_bytes = quotient(h, p) ? 2 : 4;
-  }
-  p.hash_size = h;
-  p.hash_words = h * entry_bytes / 4;
-  const size_t pw = other + size_t(p.hash_words) * 4;
   // resident warps the register file allows: the three-in-flight raw kernels are built for 3 x 256 threads,
   // everything else (SQ spaces, rows above 128 chunks) for 2 x 256
   const int reg_warps = std::min(max_warps, (quant == AB_QUANT_NONE && nchunks <= 128) ? 8 * AB_MINBLOCKS : 16);
+  // Full register-limited occupancy under a 196 KB carve-out is worth a tighter table (the step from 24 to
+  // 20 warps costs ~25 % at ef 100): shrink down to 1.3 / 1.7 of the wanted size for it. Below 12 resident
+  // warps, shrink further and let long queries continue in their global bitmap.
+  auto fit_entries = [&](size_t limit, int warps) -> uint32_t {
+    const size_t ctas = (warps + 7) / 8;
+    const size_t total = ctas * (cta_fixed + 1024) + size_t(warps) * other;
+    if (limit <= total) return 0;
+    return static_cast<uint32_t>((limit - total) / warps / entry_bytes) & ~63u;
+  };
+  const uint32_t h_full = fit_entries(std::min(smem_limit, size_t(196) * 1024), reg_warps);
+  const uint32_t h_min = std::max(entry_bytes == 2 ? 2048u : 512u, (static_cast<uint32_t>(float(h) * (1.3f / 1.7f)) + 63u) & ~63u);
+  if (h_full < h && h_full >= h_min) {
+    h = h_full;
+  } else {
+    const uint32_t h12 = fit_entries(smem_limit, 12);
+    if (h12 < h) h = std::max(512u, h12);
+  }
+  entry_bytes = quotient(h, p) ? 2 : 4;
+  p.hash_size = h;
+  p.hash_words = h * entry_bytes / 4;
+  const size_t pw = other + size_t(p.hash_words) * 4;
   // CTA size: whatever packs the most warps into the SM (each CTA also pays cta_fixed + 1 KB of reserved
   // shared memory). The unified L1 / shared-memory array also stages the row loads in flight, and the step
   // from a 196 KB to a 228 KB carve-out halves what is left for that (60 -> 28 KB): stay at or below 196 KB
