@@ -237,6 +237,38 @@ def test_visited_spill_to_bitmap_is_exact(cabi, orc, small_sets):
     assert np.array_equal(ix.batch_search(q[:50], 10, 1500), want)
 
 
+def test_visited_table_formats_agree(cabi, tmp_path):
+    """16-bit quotient entries, 32-bit id entries, a table far too small (everything continues in the bitmap) and a
+    table whose displacement range overflows must all give the same traversal, bit for bit."""
+    import subprocess
+    import sys
+    from alayalite_b200.synthetic import low_rank
+    n, dim = 30000, 32
+    base, q = low_rank(n, dim, 300, 8, seed=5)
+    ix = cabi.NativeIndex("l2", "none", n)
+    ix.fit(base, 60)
+    folder = tmp_path / "idx"
+    folder.mkdir()
+    ix.save(str(folder / "g.index"), str(folder / "g.data"))
+    np.save(folder / "queries.npy", q)
+    np.save(folder / "n.npy", np.array(n))
+    probe = os.path.join(os.path.dirname(__file__), "_visited_probe.py")
+    runs = {}
+    for name, env in {"default": {}, "ids32": {"AB_HASH16": "0"}, "tiny16": {"AB_HASH_FACTOR": "0.05"},
+                      "tiny32": {"AB_HASH16": "0", "AB_HASH_FACTOR": "0.05"}}.items():
+        out = str(tmp_path / f"{name}.npz")
+        r = subprocess.run([sys.executable, probe, str(folder), out, "16", "64", "300"], env={**os.environ, **env},
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs[name] = np.load(out)
+    for ef in (16, 64, 300):
+        for name in ("ids32", "tiny16", "tiny32"):
+            assert np.array_equal(runs[name][f"ids{ef}"], runs["default"][f"ids{ef}"]), (name, ef)
+            assert np.array_equal(runs[name][f"dist{ef}"], runs["default"][f"dist{ef}"]), (name, ef)
+    assert int(runs["tiny16"]["bitmap300"]) > 0 and int(runs["tiny32"]["bitmap300"]) > 0
+    assert int(runs["default"]["bitmap64"]) == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # brute force
 @pytest.mark.parametrize("metric", ["l2", "ip"])
