@@ -22,6 +22,7 @@ SYMBOLS = [
     "ab_index_create", "ab_index_destroy", "ab_index_fit", "ab_index_search", "ab_index_batch_search",
     "ab_index_batch_search_with_distance", "ab_index_insert", "ab_index_remove", "ab_index_get_data_by_id",
     "ab_index_get_dim", "ab_index_get_size", "ab_index_save", "ab_index_load", "ab_index_batch_search_device",
+    "ab_index_batch_search_scatter_device",
     "ab_index_fit_spaces", "ab_index_set_graph", "ab_index_build_graph", "ab_index_graph_info", "ab_index_get_graph",
     "ab_index_get_codes", "ab_index_search_stats", "ab_index_batch_traverse", "ab_distance_pairs", "ab_quant_fit_encode",
     "ab_normalize_rows", "ab_bruteforce_topk", "ab_bruteforce_topk_device", "ab_merge_topk_device", "ab_last_error",
@@ -183,6 +184,16 @@ class NativeIndex:
     def batch_search_device(self, d_queries, nq, topk, ef, d_out_ids, d_out_dist=None, rerank=True, stream=None):
         check(lib().ab_index_batch_search_device(self.h, _vp(d_queries), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef), C.c_int32(int(rerank)),
                                                  _vp(d_out_ids), _vp(d_out_dist), _vp(stream)))
+
+    def batch_search_scatter_device(self, d_queries, nq, topk, ef, d_out_ids, d_out_dist, id_offset, slot, dest_ids, dest_dist,
+                                    rerank=True, stream=None):
+        """dest_ids / dest_dist: device addresses of the [slots, nq, topk] gather buffers (one per rank, peer mapped)."""
+        n = len(dest_ids)
+        a_ids = (C.c_uint64 * n)(*[int(x) for x in dest_ids])
+        a_dist = (C.c_uint64 * n)(*[int(x) for x in dest_dist])
+        check(lib().ab_index_batch_search_scatter_device(self.h, _vp(d_queries), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef),
+                                                         C.c_int32(int(rerank)), _vp(d_out_ids), _vp(d_out_dist), C.c_uint32(id_offset),
+                                                         C.c_uint32(slot), C.c_uint32(n), a_ids, a_dist, _vp(stream)))
 
     def traverse(self, queries, ef):
         q = _f32(queries)

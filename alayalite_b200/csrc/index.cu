@@ -156,7 +156,7 @@ void index_download_graph(ab_index *ix, uint32_t *adj, uint32_t *levels, uint32_
 
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream) {
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Scatter *scatter) {
   AB_CHECK(ix->has_graph, AB_ERR_STATE, "index is not fitted or loaded");
   AB_CHECK(topk >= 1 && ef >= 1, AB_ERR_INVALID, "topk and ef must be positive");
   // the reference reads uninitialised pool slots when topk > ef (SURVEY.md 8b "Errors"); rejected here
@@ -217,6 +217,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   a.bitmaps = ix->w_bitmaps.p;
   a.bitmap_words = words;
   a.stats = ix->w_stats.p;
+  if (scatter != nullptr && !need_rerank) a.scatter = *scatter;
   launch_search(quant, plan, a, stream);
   ix->last_ef = ef;
 
@@ -236,6 +237,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
     r.cand_ids = ix->w_cand.p;
     r.out_ids = d_out_ids;
     r.out_dist = d_out_dist;
+    if (scatter != nullptr) r.scatter = *scatter;
     launch_rerank(r, ix->sm_count, stream);
   }
 }
@@ -469,6 +471,30 @@ int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64
     use_device(index);
     cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, ordered with the caller's work
     index_search_device(index, d_queries, nq, topk, ef, rerank != 0, d_out_ids, d_out_dist, nullptr, nullptr, nullptr, s);
+  });
+}
+
+int ab_index_batch_search_scatter_device(ab_index *index, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef,
+                                         int32_t rerank, uint32_t *d_out_ids, float *d_out_dist, uint32_t id_offset,
+                                         uint32_t slot, uint32_t n_dest, const uint64_t *dest_ids, const uint64_t *dest_dist,
+                                         void *stream) {
+  return guarded([&] {
+    AB_CHECK(index != nullptr && d_queries && d_out_ids, AB_ERR_INVALID, "null argument");
+    AB_CHECK(n_dest >= 1 && n_dest <= static_cast<uint32_t>(kMaxDest) && dest_ids && dest_dist, AB_ERR_INVALID,
+             "scatter needs 1..16 destination buffers");
+    Scatter sc{};
+    sc.n_dest = static_cast<int>(n_dest);
+    sc.slot = slot;
+    sc.id_offset = id_offset;
+    for (uint32_t p = 0; p < n_dest; p++) {
+      AB_CHECK(dest_ids[p] != 0 && dest_dist[p] != 0, AB_ERR_INVALID, "null destination buffer");
+      sc.ids[p] = reinterpret_cast<uint32_t *>(static_cast<uintptr_t>(dest_ids[p]));
+      sc.dist[p] = reinterpret_cast<float *>(static_cast<uintptr_t>(dest_dist[p]));
+    }
+    std::lock_guard<std::mutex> lock(index->mu);
+    use_device(index);
+    index_search_device(index, d_queries, nq, topk, ef, rerank != 0, d_out_ids, d_out_dist, nullptr, nullptr, nullptr,
+                        static_cast<cudaStream_t>(stream), &sc);
   });
 }
 

@@ -143,6 +143,17 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
   return is_new;
 }
 
+// one (id, distance) of the final list of query qi -> slot `slot` of every rank's gather buffer (peer stores)
+__device__ __forceinline__ void scatter_store(const Scatter &sc, uint32_t nq, uint32_t topk, uint32_t qi, uint32_t pos,
+                                              uint32_t id, float dist) {
+  if (sc.n_dest == 0) return;
+  const size_t o = (size_t(sc.slot) * nq + qi) * topk + pos;
+  for (int p = 0; p < sc.n_dest; p++) {
+    sc.ids[p][o] = id + sc.id_offset;
+    sc.dist[p][o] = dist;
+  }
+}
+
 // LinearPool::insert (query_utils.hpp:254-272); warp-collective, all arguments warp-uniform.
 // `expanded` inserts an entry that already carries the expanded flag (the hop that is about to run, see
 // the main loop): it never becomes the cursor, and pushes the cursor one slot right when it lands at or
@@ -560,8 +571,11 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     // ---- results ----------------------------------------------------------------------------
     for (uint32_t i = lane; i < a.topk; i += 32) {
       const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
-      a.out_ids[size_t(qi) * a.topk + i] = in ? (ws.pool[i].y & kIdMask) : 0u;
-      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = in ? __uint_as_float(ws.pool[i].x) : 0.f;
+      const uint32_t rid = in ? (ws.pool[i].y & kIdMask) : 0u;
+      const float rd = in ? __uint_as_float(ws.pool[i].x) : 0.f;
+      a.out_ids[size_t(qi) * a.topk + i] = rid;
+      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = rd;
+      scatter_store(a.scatter, a.nq, a.topk, qi, i, rid, rd);
     }
     if (a.pool_ids) {
       for (int i = lane; i < ef; i += 32) {
@@ -659,6 +673,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
       if (rank < a.topk) {
         a.out_ids[size_t(qi) * a.topk + rank] = ii;
         if (a.out_dist) a.out_dist[size_t(qi) * a.topk + rank] = di;
+        scatter_store(a.scatter, a.nq, a.topk, qi, rank, ii, di);
       }
     }
     __syncwarp();

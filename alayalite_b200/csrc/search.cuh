@@ -5,6 +5,18 @@
 namespace ab {
 
 // Everything the traversal kernel reads, by value. Device pointers unless noted.
+// Multi-GPU exchange fused into the kernel that produces the final lists: besides out_ids / out_dist the
+// results (ids + id_offset) are stored straight into the [slots, nq, topk] gather buffers of every rank of
+// the box -- peer memory mapped over NVLink -- at slot `slot`, so the transfer overlaps the search.
+constexpr int kMaxDest = 16;
+struct Scatter {
+  int n_dest;  // 0 = off
+  uint32_t slot;
+  uint32_t id_offset;
+  uint32_t *ids[kMaxDest];
+  float *dist[kMaxDest];
+};
+
 struct SearchArgs {
   // search space rows: raw floats or SQ codes, row stride in bytes (multiple of 64)
   const uint8_t *rows;
@@ -36,6 +48,7 @@ struct SearchArgs {
   uint32_t *pool_ids;  // [nq, ef] or null
   float *pool_dist;    // [nq, ef] or null
   uint32_t *pool_sizes;
+  Scatter scatter;
   // scheduling + visited set
   uint32_t *work_counter;       // zeroed before launch
   // visited-set table, filled in by launch_search from the plan
@@ -63,6 +76,7 @@ struct RerankArgs {
   const uint32_t *cand_ids;  // [nq, topk] search-space top-k
   uint32_t *out_ids;         // [nq, topk]
   float *out_dist;           // [nq, topk] or null
+  Scatter scatter;
 };
 
 // Launch configuration chosen on the host (search.cu)

@@ -292,11 +292,11 @@ def ours_arm(args, rank, world, local_rank):
         for _ in range(args.steps):
             flush.zero_()
             ev[0].record()
-            ix.batch_search_device(d_q.data_ptr(), NQ, TOPK, ef, d_ids.data_ptr(), d_dist.data_ptr(), True, stream)
-            ev[1].record()
-            if world > 1:
-                d_ids += id_offset
-                sh.exchange(d_ids, d_dist, buf, stream)
+            if world == 1:
+                ix.batch_search_device(d_q.data_ptr(), NQ, TOPK, ef, d_ids.data_ptr(), d_dist.data_ptr(), True, stream)
+                ev[1].record()
+            else:  # search (storing into every rank's gather buffer) + barrier + merge
+                sh.batch_search_device(d_q, TOPK, ef, stream, after_search=ev[1].record)
             ev[2].record()
             torch.cuda.synchronize()
             kernel_times.append(ev[0].elapsed_time(ev[1]))
@@ -355,7 +355,7 @@ def ours_arm(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "ef": ef, "recall_at_10": rec, "vectors_total": N_BASE * world, "shards": world,
+        "config": {"workload": WORKLOAD, "ef": ef, "recall_at_10": rec, "vectors_total": N_BASE * world, "shards": world, "exchange": sh.exchange_kind,
                    "timing": "CUDA events per step on the launching stream; 256 MB L2 flush between steps; index 640 MB > 126 MB L2",
                    "build_s": build_s, "index": built, "unit_note": "value counts (query, shard) searches; merged_qps is the end-user rate" if world > 1 else "1 shard: value == merged_qps"},
         "merged_qps": NQ * args.steps / (total_ms * 1e-3),

@@ -115,6 +115,16 @@ int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64
                                  uint32_t ef, int32_t rerank, uint32_t *d_out_ids, float *d_out_dist,
                                  void *stream);
 
+/* Multi-GPU (no counterpart in the reference): the same search, whose kernel additionally stores
+ * every final (id + id_offset, distance) into slot `slot` of n_dest gather buffers laid out [slots, nq, topk]
+ * -- dest_ids / dest_dist are HOST arrays of n_dest (<= 16) device addresses, normally one buffer per rank of
+ * the box mapped into this process as peer memory -- so the shard exchange rides on the search itself and
+ * only a barrier + ab_merge_topk_device remain. d_out_ids / d_out_dist receive the local lists as usual. */
+int ab_index_batch_search_scatter_device(ab_index *index, const float *d_queries, uint64_t nq, uint32_t topk,
+                                         uint32_t ef, int32_t rerank, uint32_t *d_out_ids, float *d_out_dist,
+                                         uint32_t id_offset, uint32_t slot, uint32_t n_dest,
+                                         const uint64_t *dest_ids, const uint64_t *dest_dist, void *stream);
+
 /* Parity / interchange hooks: split fit into "spaces" and "graph" so that a graph built elsewhere
  * (the reference on the CPU) can be searched on the GPU and vice versa.                          */
 int ab_index_fit_spaces(ab_index *index, const float *data, uint64_t n, uint32_t dim);
