@@ -97,6 +97,9 @@ struct SearchPlan {
 SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
                        int sm_count, size_t smem_limit);
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
+// per-quantisation translation units (search_sq8.cu / search_sq4.cu); args already completed by launch_search
+void launch_search_sq8(bool ip, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
+void launch_search_sq4(bool ip, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
 void launch_rerank(const RerankArgs &args, int sm_count, cudaStream_t stream);
 
 }  // namespace ab

@@ -1,0 +1,609 @@
+// Device code of the traversal kernel + its launcher, shared by the translation units that instantiate it
+// (search.cu: raw rows; search_sq8.cu / search_sq4.cu: quantised spaces) so that they compile in parallel.
+#pragma once
+#include <cfloat>
+#include <cstdlib>
+
+#include "distance.cuh"
+#include "search.cuh"
+
+namespace ab {
+
+namespace {
+
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kR = 32;  // level-0 degree (reference: params_.max_nbrs_ is always 32 from Python)
+
+struct WarpSmem {
+  float *q_raw;       // raw query (raw space only)
+  uint8_t *q_code;    // encoded query (SQ only)
+  uint2 *pool;        // [ef + 1] entries {distance bits, id | expanded flag}
+  uint32_t *hash;     // [hash_size]
+  uint32_t *cand;     // [32] candidate ids of the current hop, compacted
+  float *cdist;       // [32] their distances
+};
+
+// Visited set of one query. Derived values (the warp's bitmap, table parameters) are recomputed from the
+// kernel arguments where needed instead of living in registers across the hot loop.
+struct Visited {
+  uint32_t *hash;
+  bool spilled;      // the hash is frozen, new ids go to the bitmap
+  bool bitmap_used;  // the warp's global bitmap holds bits and must be cleared after the query
+};
+
+// multiply-shift range reduction: any table size, no power-of-two rounding of the shared-memory footprint
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t size) { return __umulhi(key * 0x9E3779B1u, size); }
+
+__device__ __forceinline__ bool bitmap_test_and_set(const SearchArgs &a, uint32_t key) {
+  uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
+  const uint32_t bit = 1u << (key & 31);
+  return (atomicOr(&bitmap[key >> 5], bit) & bit) == 0;
+}
+
+// Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
+// The probe loop is driven by a warp vote, so the warp stays converged (a per-lane probe loop leaves the
+// lanes split under independent thread scheduling, and every later warp-level primitive then takes the
+// compiler's slow divergent path).
+//
+// Two table formats, both exact (never a false "visited", never a false "new"):
+//  * 32-bit entries holding the id itself;
+//  * 16-bit entries (a.hash_rbits > 0) when the id range is small enough relative to the table: the id is
+//    scrambled by a bijection of the b-bit id space (odd multiplier mod 2^b), the table slot is the scaled
+//    scramble, and the entry keeps what the slot does not already say -- the position inside the slot's
+//    bucket of the id space (r, rbits bits) and the displacement from the home slot (linear probing). An
+//    entry equal to (displacement, r) at slot home + displacement can only belong to this id. Half the
+//    shared memory per warp, which matters twice: more resident warps, and more of the unified L1/shared
+//    array left to stage loads in flight. A probe that runs out of displacement range falls through to
+//    the warp's bitmap (exact, rare).
+__device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t key, bool active) {
+  const uint32_t hsize = a.hash_size;
+  bool is_new = false;
+  bool pending = active;
+  bool to_bitmap = false;
+  if (a.hash_rbits != 0) {
+    const uint32_t x = (key * 0x9E3779B1u) << a.hash_xshift;
+    uint32_t slot = __umulhi(x, hsize);
+    uint32_t code = __umulhi(x * hsize, a.hash_rmul);  // displacement 0
+    const uint32_t dstep = 1u << a.hash_rbits;
+    // Probe with plain reads; only an empty slot is claimed, with a 32-bit CAS on the word that holds it
+    // (a failed CAS -- the slot or its neighbour half changed meanwhile -- re-reads the same slot).
+    while (__any_sync(kFull, pending)) {
+      if (pending) {
+        const uint32_t sh = (slot & 1u) << 4;
+        const uint32_t w = vs.hash[slot >> 1];
+        const uint32_t cur = (w >> sh) & 0xFFFFu;
+        bool advance = true;
+        if (cur == 0xFFFFu) {
+          if (!vs.spilled) {
+            advance = false;
+            if (atomicCAS(&vs.hash[slot >> 1], w, w ^ ((0xFFFFu ^ code) << sh)) == w) {
+              is_new = true;
+              pending = false;
+            }
+          } else {
+            to_bitmap = true;
+            pending = false;
+          }
+        } else if (cur == code) {
+          pending = false;
+        }
+        if (pending && advance) {
+          slot = slot + 1 == hsize ? 0u : slot + 1;
+          code += dstep;
+          if (code >= a.hash_dlimit) {  // out of displacement range
+            pending = false;
+            to_bitmap = true;
+          }
+        }
+      }
+    }
+  } else {
+    uint32_t slot = hash_slot(key, hsize);
+    while (__any_sync(kFull, pending)) {
+      if (pending) {
+        uint32_t old;
+        if (!vs.spilled) {
+          old = atomicCAS(&vs.hash[slot], kEmptyId, key);
+          is_new = old == kEmptyId;
+        } else {
+          old = vs.hash[slot];
+          to_bitmap = old == kEmptyId;
+        }
+        pending = !(old == kEmptyId || old == key);
+        slot = slot + 1 == hsize ? 0u : slot + 1;
+      }
+    }
+  }
+  if (__any_sync(kFull, to_bitmap)) {
+    if (to_bitmap) is_new = bitmap_test_and_set(a, key);
+    vs.bitmap_used = true;
+    __syncwarp();
+  }
+  return is_new;
+}
+
+// one (id, distance) of the final list of query qi -> slot `slot` of every rank's gather buffer (peer stores)
+__device__ __forceinline__ void scatter_store(const Scatter &sc, uint32_t nq, uint32_t topk, uint32_t qi, uint32_t pos,
+                                              uint32_t id, float dist) {
+  if (sc.n_dest == 0) return;
+  const size_t o = (size_t(sc.slot) * nq + qi) * topk + pos;
+  for (int p = 0; p < sc.n_dest; p++) {
+    sc.ids[p][o] = id + sc.id_offset;
+    sc.dist[p][o] = dist;
+  }
+}
+
+// LinearPool::insert (query_utils.hpp:254-272); warp-collective, all arguments warp-uniform.
+// `expanded` inserts an entry that already carries the expanded flag (the hop that is about to run, see
+// the main loop): it never becomes the cursor, and pushes the cursor one slot right when it lands at or
+// before it.
+__device__ __forceinline__ void pool_insert(uint2 *pool, int &size, int &cur, int ef, float d, uint32_t v, int lane,
+                                            bool expanded = false) {
+  int pos;  // upper bound: number of entries with dist <= d
+  const int nsize = min(size + 1, ef);
+  if (ef <= 64) {
+    // the pool fits two entries per lane: read everything first, then every entry behind the insert
+    // position moves one slot to the right in a single step
+    const int i1 = lane + 32;
+    const uint2 e0 = pool[lane];
+    uint2 e1 = make_uint2(0u, 0u);
+    if (size > 32 && i1 < size) e1 = pool[i1];
+    pos = __popc(__ballot_sync(kFull, lane < size && __uint_as_float(e0.x) <= d));
+    if (size > 32) pos += __popc(__ballot_sync(kFull, i1 < size && __uint_as_float(e1.x) <= d));
+    __syncwarp();
+    if (lane >= pos && lane < size && lane + 1 < nsize) pool[lane + 1] = e0;
+    if (size > 32 && i1 >= pos && i1 < size && i1 + 1 < nsize) pool[i1 + 1] = e1;
+    if (lane == 0) pool[pos] = make_uint2(__float_as_uint(d), v);
+    __syncwarp();
+  } else {
+    pos = 0;
+    for (int base = 0; base < size; base += 32) {
+      const int i = base + lane;
+      const uint32_t b = __ballot_sync(kFull, i < size && __uint_as_float(pool[i].x) <= d);
+      pos += __popc(b);
+      if (b != kFull) break;
+    }
+    for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 > pos; base -= 32) {
+      const int i = base + lane;
+      const bool mv = i > pos && i < nsize;
+      uint2 t = make_uint2(0u, 0u);
+      if (mv) t = pool[i - 1];
+      __syncwarp();
+      if (mv) pool[i] = t;
+      __syncwarp();
+    }
+    if (lane == 0) pool[pos] = make_uint2(__float_as_uint(d), v);
+    __syncwarp();
+  }
+  size = nsize;
+  if (expanded) {
+    if (pos <= cur) cur = min(cur + 1, nsize);
+  } else if (pos < cur) {
+    cur = pos;
+  }
+}
+
+// order-preserving map float -> uint32 (for warp-wide integer min)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+// Evaluate the search-space distance of the candidate held by every lane with want == true.
+// Generic path: query in shared memory, any space (distance.cuh row_distance).
+template <int QUANT, bool IP, int TPV, int MAXC>
+__device__ __forceinline__ float eval_lanes(const SearchArgs &a, const WarpSmem &ws, const QuerySmem &qs,
+                                            uint32_t v, bool want, int lane) {
+  constexpr int G = 32 / TPV;
+  const uint32_t mask = __ballot_sync(kFull, want);
+  const int cnt = __popc(mask);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  if (want) ws.cand[rank] = v;
+  __syncwarp();
+  const int g = lane / TPV, lg = lane % TPV;
+  for (int base = 0; base < cnt; base += G) {
+    const int k = base + g;
+    const bool act = k < cnt;
+    const uint32_t cv = act ? ws.cand[k] : 0u;
+    float d = row_distance<QUANT, IP, TPV, MAXC>(a.rows + size_t(cv) * size_t(a.row_stride), a.nchunks, lg, qs, act);
+    if (act && lg == 0) ws.cdist[k] = d;
+  }
+  __syncwarp();
+  const float out = want ? ws.cdist[rank] : FLT_MAX;
+  __syncwarp();
+  return out;
+}
+
+// Raw-space fast path: query slice in registers, packed fp32 math, two candidates per group in
+// flight (distance.cuh raw_distance2).
+template <bool IP, int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ float eval_lanes_raw(const SearchArgs &a, const WarpSmem &ws, const U64x2 (&q)[CPL], uint32_t v,
+                                                bool want, int lane) {
+  constexpr int G = 32 / TPV;
+  const uint32_t mask = __ballot_sync(kFull, want);
+  const int cnt = __popc(mask);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  if (want) ws.cand[rank] = v;
+  __syncwarp();
+  const int g = lane / TPV, lg = lane % TPV;
+  const uint8_t *lane_base = a.rows + lg * 16;
+  for (int base = 0; base < cnt; base += 2 * G) {
+    const int k0 = base + g, k1 = k0 + G;
+    const bool act0 = k0 < cnt, act1 = k1 < cnt;
+    const uint32_t c0 = ws.cand[act0 ? k0 : 0];
+    float d0;
+    uint32_t c1 = c0;
+    if (cnt - base > G) {  // warp-uniform: a second candidate exists for at least one group
+      c1 = ws.cand[act1 ? k1 : 0];
+      raw_distance2<IP, TPV, CPL, EXACT>(lane_base + size_t(c0) * a.row_stride, lane_base + size_t(c1) * a.row_stride, q,
+                                         a.nchunks, lg, d0);
+    } else {  // every lane of the group gets the sum
+      d0 = raw_distance1<IP, TPV, CPL, EXACT>(lane_base + size_t(c0) * a.row_stride, q, a.nchunks, lg);
+    }
+    // lane 0 of a group ends up with the first candidate's distance, lane 1 with the second's
+    if (lg < 2) {
+      const int k = lg ? k1 : k0;
+      if (k < cnt) ws.cdist[k] = d0;
+    }
+  }
+  __syncwarp();
+  const float out = want ? ws.cdist[rank] : FLT_MAX;
+  __syncwarp();
+  return out;
+}
+
+// Three candidates per group in flight, query read from shared memory after the loads are issued
+// (distance.cuh raw_distance_multi / sq_distance_multi). Used when a row is at most 4 chunks per lane.
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT, int NC>
+__device__ __forceinline__ float multi_distance(const uint8_t *r0, const uint8_t *r1, const uint8_t *r2, const QuerySmem &qs,
+                                                int nchunks, int lg) {
+  if constexpr (QUANT == AB_QUANT_NONE) {
+    return raw_distance_multi<IP, TPV, CPL, EXACT, NC>(r0, r1, r2, qs.q_raw, nchunks, lg);
+  } else {
+    return sq_distance_multi<QUANT, IP, TPV, CPL, NC>(r0, r1, r2, qs, nchunks, lg);
+  }
+}
+
+#ifndef AB_HASH_FACTOR
+#define AB_HASH_FACTOR 1.34f
+#endif
+#ifndef AB_INFLIGHT
+#define AB_INFLIGHT 3
+#endif
+#ifndef AB_MINBLOCKS
+#define AB_MINBLOCKS 3
+#endif
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
+__device__ __forceinline__ float eval_lanes_multi(const SearchArgs &a, const WarpSmem &ws, const QuerySmem &qs, uint32_t v,
+                                                  bool want, int lane) {
+  constexpr int G = 32 / TPV;
+  const uint32_t mask = __ballot_sync(kFull, want);
+  const int cnt = __popc(mask);
+  const int rank = __popc(mask & ((1u << lane) - 1));
+  if (want) ws.cand[rank] = v;
+  __syncwarp();
+  const int g = lane / TPV, lg = lane % TPV;
+  const uint8_t *lane_base = a.rows + lg * 16;
+  for (int base = 0; base < cnt; base += AB_INFLIGHT * G) {
+    const int rem = cnt - base;  // warp-uniform
+    const int k0 = base + g, k1 = k0 + G, k2 = k1 + G;
+    const uint8_t *r0 = lane_base + size_t(ws.cand[k0 < cnt ? k0 : 0]) * a.row_stride;
+    if (AB_INFLIGHT > 2 && rem > 2 * G) {
+      const uint8_t *r1 = lane_base + size_t(ws.cand[k1 < cnt ? k1 : 0]) * a.row_stride;
+      const uint8_t *r2 = lane_base + size_t(ws.cand[k2 < cnt ? k2 : 0]) * a.row_stride;
+      const float d = multi_distance<QUANT, IP, TPV, CPL, EXACT, 3>(r0, r1, r2, qs, a.nchunks, lg);
+      const int k = k0 + lg * G;  // lanes 0..2 of the group hold candidates 0..2
+      if (lg < 3 && k < cnt) ws.cdist[k] = d;
+    } else if (rem > G) {
+      const uint8_t *r1 = lane_base + size_t(ws.cand[k1 < cnt ? k1 : 0]) * a.row_stride;
+      const float d = multi_distance<QUANT, IP, TPV, CPL, EXACT, 2>(r0, r1, r1, qs, a.nchunks, lg);
+      const int k = k0 + lg * G;
+      if (lg < 2 && k < cnt) ws.cdist[k] = d;
+    } else {
+      const float d = multi_distance<QUANT, IP, TPV, CPL, EXACT, 1>(r0, r0, r0, qs, a.nchunks, lg);
+      if (lg == 0 && k0 < cnt) ws.cdist[k0] = d;
+    }
+  }
+  __syncwarp();
+  const float out = want ? ws.cdist[rank] : FLT_MAX;
+  __syncwarp();
+  return out;
+}
+
+// CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
+// CPL == 0 is the generic path for any space.
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
+__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? AB_MINBLOCKS : 2) beam_search_kernel(const SearchArgs a) {
+  constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
+  constexpr int MAXC = 8;
+  // three candidates in flight, query from shared memory (raw rows, and SQ codes with packed arithmetic)
+  constexpr bool FAST3 = CPL > 0 && CPL <= 4;
+  constexpr int QREGS = (FAST && !FAST3) ? CPL : 1;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = lane_id();
+  // redux lands in a uniform register: the compiler then knows every per-warp address below is warp-uniform
+  const int warp = static_cast<int>(__reduce_min_sync(kFull, threadIdx.x >> 5));
+  const int warps = blockDim.x >> 5;
+
+  // ---- carve shared memory: CTA-wide tables, then one region per warp -------------------------
+  float *s_scale = reinterpret_cast<float *>(smem);
+  float *s_vmin = s_scale + (QUANT != AB_QUANT_NONE ? a.table_len : 0);
+  size_t off = (QUANT != AB_QUANT_NONE ? size_t(a.table_len) * 8 : 0);
+  const size_t q_bytes = size_t(a.nchunks) * 16;
+  const size_t pool_bytes = round_up16(size_t(a.ef + 1) * 8);
+  const size_t per_warp = 256 + q_bytes + pool_bytes + size_t(a.hash_words) * 4;
+  uint8_t *wbase = smem + off + size_t(warp) * per_warp;
+  WarpSmem ws;
+  ws.cand = reinterpret_cast<uint32_t *>(wbase);
+  ws.cdist = reinterpret_cast<float *>(wbase + 128);
+  ws.q_raw = reinterpret_cast<float *>(wbase + 256);
+  ws.q_code = wbase + 256;
+  ws.pool = reinterpret_cast<uint2 *>(wbase + 256 + q_bytes);
+  ws.hash = reinterpret_cast<uint32_t *>(wbase + 256 + q_bytes + pool_bytes);
+
+  if (QUANT != AB_QUANT_NONE) {
+    for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) {
+      s_scale[i] = a.scale[i];
+      s_vmin[i] = a.vmin[i];
+    }
+    __syncthreads();
+  }
+  QuerySmem qs;
+  qs.q_raw = ws.q_raw;
+  qs.q_code = ws.q_code;
+  qs.scale = s_scale;
+  qs.vmin = s_vmin;
+
+  Visited vs;
+  vs.hash = ws.hash;
+  const int ef = static_cast<int>(a.ef);
+
+  while (true) {
+    if (lane == 0) ws.cand[0] = atomicAdd(a.work_counter, 1u);
+    __syncwarp();
+    const uint32_t qi = ws.cand[0];
+    __syncwarp();
+    if (qi >= a.nq) break;
+    const float *qg = a.queries + size_t(a.q_ids ? a.q_ids[qi] : qi) * a.q_stride;
+
+    // ---- stage the query -------------------------------------------------------------------
+    if (QUANT == AB_QUANT_NONE) {
+      // RawSpace::QueryComputer (raw_space.hpp:264-274): aligned copy, COS normalises first
+      const int nfl = a.nchunks * 4;
+      float ss = 0.f;
+      for (int i = lane; i < nfl; i += 32) {
+        const float x = i < static_cast<int>(a.dim) ? qg[i] : 0.f;
+        ws.q_raw[i] = x;
+        ss = fmaf(x, x, ss);
+      }
+      if (a.metric == AB_METRIC_COS && !a.q_prenormalized) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+        const float inv = static_cast<float>(1.0 / static_cast<double>(sqrtf(ss)));  // data_utils.hpp:36-46
+        __syncwarp();
+        for (int i = lane; i < nfl; i += 32) ws.q_raw[i] *= inv;
+      }
+    } else if (QUANT == AB_QUANT_SQ8) {
+      // SQ8Space::QueryComputer (sq8_space.hpp:264-269): encode the (un-normalised) query
+      const int nb = a.nchunks * 16;
+      for (int i = lane; i < nb; i += 32) {
+        uint32_t c = 0;
+        if (i < static_cast<int>(a.dim)) c = sq_quantize(qg[i], a.qmin[i], a.qmax[i], 255.f);
+        ws.q_code[i] = static_cast<uint8_t>(c);
+      }
+    } else {
+      // SQ4Space::QueryComputer (sq4_space.hpp:265-270) + SQ4Quantizer::encode (sq4.hpp:139-149)
+      const int nb = a.nchunks * 16;
+      for (int j = lane; j < nb; j += 32) {
+        uint32_t first = 0, second = 0;
+        const int i = 2 * j;
+        if (i < static_cast<int>(a.dim)) first = sq_quantize(qg[i], a.qmin[i], a.qmax[i], 15.f);
+        if (i + 1 < static_cast<int>(a.dim)) second = sq_quantize(qg[i + 1], a.qmin[i + 1], a.qmax[i + 1], 15.f);
+        ws.q_code[j] = static_cast<uint8_t>((first << 4) | second);
+      }
+    }
+    for (uint32_t i = lane; i < a.hash_words / 4; i += 32) reinterpret_cast<uint4 *>(ws.hash)[i] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
+    for (int i = lane; i <= ef; i += 32) {
+      ws.pool[i] = make_uint2(0u, 0u);
+    }
+    __syncwarp();
+
+    int size = 0, cur = 0;
+    uint32_t nvis = 0;
+    uint32_t ndc = 0, hops = 0, ndc_ov = 0;  // per query: far below 2^32
+    vs.spilled = false;
+    vs.bitmap_used = false;
+
+    // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
+    uint32_t u = a.ep;
+    U64x2 qreg[QREGS];
+    if (FAST && !FAST3) load_query_regs<TPV, QREGS, EXACT>(ws.q_raw, a.nchunks, lane % TPV, qreg);
+    // distance of the candidate in every lane with WANT; afterwards ws.cand / ws.cdist hold the wanted ids and
+    // distances compacted in lane order. Warp-uniform values are re-read from there (uniform shared-memory
+    // loads) rather than shuffled, which keeps the control flow provably convergent for the compiler.
+    auto eval = [&](uint32_t id, bool want) -> float {
+      float dd;
+      if constexpr (FAST3) {
+        dd = eval_lanes_multi<QUANT, IP, TPV, CPL, EXACT>(a, ws, qs, id, want, lane);
+      } else if constexpr (FAST) {
+        dd = eval_lanes_raw<IP, TPV, QREGS, EXACT>(a, ws, qreg, id, want, lane);
+      } else {
+        dd = eval_lanes<QUANT, IP, TPV, MAXC>(a, ws, qs, id, want, lane);
+      }
+      if (QUANT == AB_QUANT_NONE && a.valid != nullptr) {
+        // RawSpace::QueryComputer returns FLT_MAX for tombstoned rows (raw_space.hpp:297-304)
+        const uint32_t wm = __ballot_sync(kFull, want);
+        if (want && ((a.valid[id >> 5] >> (id & 31)) & 1u) == 0) {
+          dd = FLT_MAX;
+          ws.cdist[__popc(wm & ((1u << lane) - 1))] = dd;
+        }
+        __syncwarp();
+      }
+      return dd;
+    };
+#define AB_EVAL(ID, WANT) eval(ID, WANT)
+    AB_EVAL(u, lane == 0);
+    float cur_d = ws.cdist[0];
+    __syncwarp();
+    ndc_ov += 1;
+    if (a.ov_off != nullptr) {
+      for (int level = static_cast<int>(a.ep_level); level > 0; --level) {
+        bool changed = true;
+        while (changed) {
+          changed = false;
+          const uint32_t row = a.ov_off[u] + static_cast<uint32_t>(level - 1);
+          const uint32_t v = a.ov_lists[size_t(row) * kR + lane];
+          const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
+          const int cnt = empties ? __ffs(empties) - 1 : kR;
+          const bool want = lane < cnt;
+          const float d = AB_EVAL(v, want);
+          ndc_ov += cnt;
+          // sequential "if (dist < cur_dist)" scan == first index attaining the minimum, if < cur_d
+          if (cnt > 0) {
+            const uint32_t key = want ? float_key(d) : 0xFFFFFFFFu;
+            const uint32_t kmin = __reduce_min_sync(kFull, key);
+            const int bl = __ffs(__ballot_sync(kFull, want && key == kmin)) - 1;  // want lanes are 0..cnt-1: rank == lane
+            const float best = ws.cdist[bl];
+            if (best < cur_d) {
+              cur_d = best;
+              u = ws.cand[bl];
+              changed = true;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) atomicAdd(&a.stats[2], static_cast<unsigned long long>(ndc_ov));
+    pool_insert(ws.pool, size, cur, ef, cur_d, u, lane);
+    visit(a, vs, u, lane == 0);
+    nvis = 1;
+    __syncwarp();
+
+    // ---- best-first search on level 0 (graph_search_job.hpp:307-331) ---------------------------
+    // Same sequence of pops and inserts as the reference, scheduled differently: once the distances of a
+    // hop are known, the next node to expand is already determined -- the closer of the first un-expanded
+    // pool entry and the best accepted candidate (ties go to the pool entry, which upper-bound insertion
+    // would have placed first) -- so its adjacency row is requested first and the pool inserts of this hop
+    // run while that load is in flight. A candidate chosen this way is inserted with its expanded flag set.
+    u = ws.pool[0].y;  // LinearPool::pop of the entry node
+    __syncwarp();
+    if (lane == 0) ws.pool[0].y = u | kCheckedBit;
+    cur = 1;
+    uint32_t v = a.adj[size_t(u) * kR + lane];
+    while (true) {
+      hops++;
+      const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
+      const int cnt = empties ? __ffs(empties) - 1 : kR;
+      if (!vs.spilled && nvis + kR > a.hash_limit) vs.spilled = true;
+      const bool is_new = visit(a, vs, v, lane < cnt);
+      const uint32_t newmask = __ballot_sync(kFull, is_new);
+      float d = FLT_MAX;
+      if (newmask) {
+        nvis += __popc(newmask);
+        d = AB_EVAL(v, is_new);
+      }
+      // A candidate that fails "d < worst" against a full pool now can only fail later too (worst never
+      // grows), so pre-filtering is exact.
+      const float worst = size == ef ? __uint_as_float(ws.pool[size - 1].x) : FLT_MAX;
+      const bool accept = is_new && (size < ef || d < worst);
+      uint32_t acc = __ballot_sync(kFull, accept);
+      const bool have_old = cur < size;
+      if (acc == 0 && !have_old) break;
+      int sel = -1;
+      if (acc) {
+        const uint32_t key = accept ? float_key(d) : 0xFFFFFFFFu;
+        const uint32_t kmin = __reduce_min_sync(kFull, key);
+        const int bl = __ffs(__ballot_sync(kFull, accept && key == kmin)) - 1;  // first neighbour attaining the minimum
+        const int rb = __popc(newmask & ((1u << bl) - 1));
+        if (!have_old || ws.cdist[rb] < __uint_as_float(ws.pool[cur].x)) {
+          sel = bl;
+          u = ws.cand[rb];
+        }
+      }
+      if (sel < 0) {
+        // LinearPool::pop (query_utils.hpp:284-293)
+        u = ws.pool[cur].y;
+        __syncwarp();
+        if (lane == 0) ws.pool[cur].y = u | kCheckedBit;
+        __syncwarp();
+        int nxt = size;
+        for (int base = cur + 1; base < size; base += 32) {
+          const int i = base + lane;
+          const uint32_t b = __ballot_sync(kFull, i < size && (ws.pool[i].y & kCheckedBit) == 0);
+          if (b) {
+            nxt = base + __ffs(b) - 1;
+            break;
+          }
+        }
+        cur = nxt;
+      }
+      const uint32_t v_next = a.adj[size_t(u) * kR + lane];
+
+      // inserts in neighbour order
+      while (acc) {
+        const int j = __ffs(acc) - 1;
+        acc &= acc - 1;
+        const int rj = __popc(newmask & ((1u << j) - 1));
+        const float dj = ws.cdist[rj];
+        const uint32_t vj = ws.cand[rj];
+        if (size == ef && dj >= __uint_as_float(ws.pool[size - 1].x)) continue;
+        pool_insert(ws.pool, size, cur, ef, dj, j == sel ? (vj | kCheckedBit) : vj, lane, j == sel);
+      }
+      // the closest un-expanded entry is the likely hop after this one: pull its adjacency row towards L2
+      if (lane == 0 && cur < size) {
+        const uint32_t nx = ws.pool[cur].y & kIdMask;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adj + size_t(nx) * kR));
+      }
+      v = v_next;
+    }
+    ndc = nvis - 1;
+
+    // ---- results ----------------------------------------------------------------------------
+    for (uint32_t i = lane; i < a.topk; i += 32) {
+      const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
+      const uint32_t rid = in ? (ws.pool[i].y & kIdMask) : 0u;
+      const float rd = in ? __uint_as_float(ws.pool[i].x) : 0.f;
+      a.out_ids[size_t(qi) * a.topk + i] = rid;
+      if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = rd;
+      scatter_store(a.scatter, a.nq, a.topk, qi, i, rid, rd);
+    }
+    if (a.pool_ids) {
+      for (int i = lane; i < ef; i += 32) {
+        a.pool_ids[size_t(qi) * a.ef + i] = i < size ? (ws.pool[i].y & kIdMask) : 0u;
+        a.pool_dist[size_t(qi) * a.ef + i] = i < size ? __uint_as_float(ws.pool[i].x) : 0.f;
+      }
+      if (lane == 0) a.pool_sizes[qi] = size;
+    }
+    if (vs.bitmap_used) {
+      // give the private bitmap back all-zero (the reference allocates + zeroes one per query)
+      uint4 *bm = reinterpret_cast<uint4 *>(a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words);
+      for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
+    }
+    if (lane == 0) {
+      atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
+      atomicAdd(&a.stats[1], static_cast<unsigned long long>(hops));
+      if (vs.bitmap_used) atomicAdd(&a.stats[3], 1ull);
+    }
+    __syncwarp();
+  }
+}
+
+#undef AB_EVAL
+
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
+void launch_one(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
+  auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT>;
+  AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes)));
+  // The unified L1 / shared-memory array also stages the row loads in flight: ask for exactly the shared memory
+  // the resident CTAs need and leave the rest to L1.
+  const size_t need = size_t(p.ctas_per_sm) * (p.smem_bytes + 1024);
+  const int pct = static_cast<int>(std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024)));
+  AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  kern<<<dim3(p.ctas), dim3(p.warps_per_cta * 32), p.smem_bytes, s>>>(a);
+}
+
+
+}  // namespace
+
+}  // namespace ab
