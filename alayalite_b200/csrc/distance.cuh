@@ -425,19 +425,20 @@ __device__ __forceinline__ float sq_distance_multi(const uint8_t *r0, const uint
       const uint32_t c0[4] = {x0[i].x, x0[i].y, x0[i].z, x0[i].w};
       const uint32_t c1[4] = {x1[NC > 1 ? i : 0].x, x1[NC > 1 ? i : 0].y, x1[NC > 1 ? i : 0].z, x1[NC > 1 ? i : 0].w};
       const uint32_t c2[4] = {x2[NC > 2 ? i : 0].x, x2[NC > 2 ? i : 0].y, x2[NC > 2 ? i : 0].z, x2[NC > 2 ? i : 0].w};
-      // table entries of this chunk: 16 (SQ8) or 32 (SQ4) dimensions -> NP / 2 float4 per word
-      const float4 *st = reinterpret_cast<const float4 *>(qs.scale) + ch * (NP * 2);
-      const float4 *mt = reinterpret_cast<const float4 *>(qs.vmin) + ch * (NP * 2);
+      // table entries of this chunk: 16 (SQ8) or 32 (SQ4) dimensions = NP * 2 float4, stored transposed
+      // ([float4 index within the chunk][chunk], see the staging loop of beam_search_kernel)
+      const float4 *st = reinterpret_cast<const float4 *>(qs.scale) + ch;
+      const float4 *mt = reinterpret_cast<const float4 *>(qs.vmin) + ch;
 #pragma unroll
       for (int w = 0; w < 4; w++) {
         unsigned long long S[NP], M[NP], Q[NP], C[NP];
 #pragma unroll
         for (int h = 0; h < NP / 2; h++) {
-          const float4 sv = st[w * (NP / 2) + h];
+          const float4 sv = st[(w * (NP / 2) + h) * nchunks];
           S[2 * h] = p2pack(sv.x, sv.y);
           S[2 * h + 1] = p2pack(sv.z, sv.w);
           if (IP) {
-            const float4 mv = mt[w * (NP / 2) + h];
+            const float4 mv = mt[(w * (NP / 2) + h) * nchunks];
             M[2 * h] = p2pack(mv.x, mv.y);
             M[2 * h + 1] = p2pack(mv.z, mv.w);
           }

@@ -342,9 +342,20 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
   ws.hash = reinterpret_cast<uint32_t *>(wbase + 256 + q_bytes + pool_bytes);
 
   if (QUANT != AB_QUANT_NONE) {
+    // The multi-candidate path reads the tables of chunk (lg + i * TPV): consecutive lanes, consecutive chunks.
+    // Stored in dimension order that is a 64 / 128-byte stride -> every 128-bit read of a quarter warp lands in
+    // the same banks. Transposed to [float4 index within the chunk][chunk] the same reads are conflict-free.
+    constexpr int DPC = QUANT == AB_QUANT_SQ8 ? 16 : 32;  // dimensions per 16-byte chunk of codes
     for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) {
-      s_scale[i] = a.scale[i];
-      s_vmin[i] = a.vmin[i];
+      int at = i;
+      if (CPL > 0) {
+        const int chunk = i / DPC, e = i % DPC;
+        at = ((e >> 2) * a.nchunks + chunk) * 4 + (e & 3);
+      }
+      if (CPL == 0 || i / DPC < a.nchunks) {
+        s_scale[at] = a.scale[i];
+        s_vmin[at] = a.vmin[i];
+      }
     }
     __syncthreads();
   }
