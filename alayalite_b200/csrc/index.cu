@@ -251,20 +251,44 @@ static void search_host(ab_index *ix, const float *queries, uint64_t nq, uint32_
   if (nq == 0) return;
   AB_CHECK(queries != nullptr && out_ids != nullptr, AB_ERR_INVALID, "null buffer");
   cudaStream_t s = ix->stream;
-  ix->w_queries.reserve(nq * ix->dim);
-  ix->w_ids.reserve(nq * topk);
-  ix->w_dist.reserve(nq * topk);
+  // Pinned (page-locked, mapped) caller buffers are used in place: the kernel reads each query once over the
+  // host link while other warps compute, and writes the few result bytes straight back, instead of a
+  // serialised copy-in / copy-out around the launch. Pageable buffers go through staging copies.
+  auto mapped = [](const void *p) -> void * {
+    cudaPointerAttributes at{};
+    if (p == nullptr || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  const float *d_q = static_cast<const float *>(mapped(queries));
+  uint32_t *d_ids = static_cast<uint32_t *>(mapped(out_ids));
+  float *d_dist = out_dist ? static_cast<float *>(mapped(out_dist)) : nullptr;
+  const bool stage_ids = d_ids == nullptr, stage_dist = out_dist != nullptr && d_dist == nullptr;
+  if (d_q == nullptr) {
+    ix->w_queries.reserve(nq * ix->dim);
+    AB_CUDA(cudaMemcpyAsync(ix->w_queries.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    d_q = ix->w_queries.p;
+  }
+  if (stage_ids) {
+    ix->w_ids.reserve(nq * topk);
+    d_ids = ix->w_ids.p;
+  }
+  if (stage_dist) {
+    ix->w_dist.reserve(nq * topk);
+    d_dist = ix->w_dist.p;
+  }
   if (pool_ids) {
     ix->w_pool_ids.reserve(nq * ef);
     ix->w_pool_dist.reserve(nq * ef);
     ix->w_pool_sizes.reserve(nq);
   }
-  AB_CUDA(cudaMemcpyAsync(ix->w_queries.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
-  index_search_device(ix, ix->w_queries.p, nq, topk, ef, rerank, ix->w_ids.p, out_dist ? ix->w_dist.p : nullptr,
+  index_search_device(ix, d_q, nq, topk, ef, rerank, d_ids, out_dist ? d_dist : nullptr,
                       pool_ids ? ix->w_pool_ids.p : nullptr, pool_ids ? ix->w_pool_dist.p : nullptr,
                       pool_ids ? ix->w_pool_sizes.p : nullptr, s);
-  AB_CUDA(cudaMemcpyAsync(out_ids, ix->w_ids.p, nq * topk * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  if (out_dist) AB_CUDA(cudaMemcpyAsync(out_dist, ix->w_dist.p, nq * topk * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (stage_ids) AB_CUDA(cudaMemcpyAsync(out_ids, ix->w_ids.p, nq * topk * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (stage_dist) AB_CUDA(cudaMemcpyAsync(out_dist, ix->w_dist.p, nq * topk * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (pool_ids) {
     AB_CUDA(cudaMemcpyAsync(pool_ids, ix->w_pool_ids.p, nq * ef * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     AB_CUDA(cudaMemcpyAsync(pool_dist, ix->w_pool_dist.p, nq * ef * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -237,6 +237,25 @@ def test_visited_spill_to_bitmap_is_exact(cabi, orc, small_sets):
     assert np.array_equal(ix.batch_search(q[:50], 10, 1500), want)
 
 
+@pytest.mark.parametrize("quant", ["none", "sq8"])
+def test_pinned_host_buffers_are_used_in_place(cabi, small_sets, quant):
+    """Pinned caller buffers are read / written by the kernels directly (no staging copies); pageable ones are
+    staged. Both routes must return the same lists."""
+    import torch
+    base, q = small_sets["lowrank"]
+    ix = cabi.NativeIndex("l2", quant, len(base))
+    ix.fit(base, 60)
+    want = ix.batch_search(q, 10, 64)  # numpy (pageable) buffers
+    qt = torch.from_numpy(np.ascontiguousarray(q)).pin_memory()
+    out = torch.full((len(q), 10), -1, dtype=torch.int32).pin_memory()
+    ix.batch_search_ptr(qt.data_ptr(), len(q), 10, 64, out.data_ptr())
+    assert np.array_equal(out.numpy().view(np.uint32), want)
+    # pinned queries, pageable output
+    out2 = np.zeros((len(q), 10), np.uint32)
+    ix.batch_search_ptr(qt.data_ptr(), len(q), 10, 64, out2.ctypes.data)
+    assert np.array_equal(out2, want)
+
+
 def test_visited_table_formats_agree(cabi, tmp_path):
     """16-bit quotient entries, 32-bit id entries, a table far too small (everything continues in the bitmap) and a
     table whose displacement range overflows must all give the same traversal, bit for bit."""
