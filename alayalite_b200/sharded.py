@@ -91,7 +91,7 @@ class ShardedIndex:
             self._peer[key] = entry
         return self._peer[key]
 
-    def _search_exchange_peer(self, d_queries, nq, topk, ef, b, pb, stream, after_search=None):
+    def _search_exchange_peer(self, d_queries, nq, topk, ef, b, pb, stream, after_search=None, out=None):
         t = self.torch
         parity = self._step & 1  # two buffer sets: a fast rank may already write step t+1 while a peer merges step t
         self._step += 1
@@ -110,18 +110,22 @@ class ShardedIndex:
                 pb["hdl"].barrier(channel=0)
         g_ids = pb["buf"][parity, 0]
         g_dist = pb["buf"][parity, 1].view(t.float32)
-        self._merge(g_dist, g_ids, nq, topk, b["m_ids"], b["m_dist"], stream)
-        return b["m_ids"], b["m_dist"]
+        m_ids = b["m_ids"] if out is None else out  # a pinned host tensor is written by the merge kernel directly
+        self._merge(g_dist, g_ids, nq, topk, m_ids, b["m_dist"], stream)
+        return m_ids, b["m_dist"]
 
-    def batch_search_device(self, d_queries, topk, ef, stream=None, after_search=None):
-        """Queries already on this rank's device (replicated). Returns device tensors (ids, dist).
+    def batch_search_device(self, d_queries, topk, ef, stream=None, after_search=None, device=None, out=None):
+        """Queries on this rank's device (replicated), or in pinned host memory the device can read in place
+        (then pass `device`). Returns device tensors (ids, dist); `out` (pinned host int32 [nq, topk]) receives the
+        merged ids directly when the peer-memory exchange is in use.
         after_search: optional callable run right after the search launch (bench.py records an event there)."""
         nq = d_queries.shape[0]
-        b = self._buffers(nq, topk, d_queries.device)
-        if self.peer_memory and d_queries.is_cuda:
-            pb = self._peer_buffers(nq, topk, d_queries.device)
+        device = d_queries.device if device is None else self.torch.device(device)
+        b = self._buffers(nq, topk, device)
+        if self.peer_memory and device.type == "cuda":
+            pb = self._peer_buffers(nq, topk, device)
             if pb is not None:
-                return self._search_exchange_peer(d_queries, nq, topk, ef, b, pb, stream, after_search)
+                return self._search_exchange_peer(d_queries, nq, topk, ef, b, pb, stream, after_search, out)
         self._search(d_queries, nq, topk, ef, b["ids"], b["dist"], stream)
         if after_search is not None:
             after_search()
@@ -129,14 +133,19 @@ class ShardedIndex:
         return self.exchange(b["ids"], b["dist"], b, stream)
 
     def batch_search(self, queries, topk, ef, out=None, device=None, stream=None):
-        """Host queries in (numpy or pinned torch tensor), merged global ids out on the host."""
+        """Host queries in (numpy or pinned torch tensor), merged global ids out on the host. Pinned tensors are
+        read (queries) and written (out) in place by the kernels; anything else is copied."""
         t = self.torch
         q = queries if isinstance(queries, t.Tensor) else t.from_numpy(np.ascontiguousarray(queries, np.float32))
-        d_q = q.to(device if device is not None else ("cuda" if t.cuda.is_available() else "cpu"), non_blocking=True)
-        ids, _ = self.batch_search_device(d_q, topk, ef, stream)
+        dev = t.device(device if device is not None else ("cuda" if t.cuda.is_available() else "cpu"))
+        in_place = dev.type == "cuda" and self.peer_memory and self._peer_buffers(q.shape[0], topk, dev) is not None
+        d_q = q if (in_place and q.is_pinned()) else q.to(dev, non_blocking=True)
+        direct_out = out if (in_place and out is not None and out.is_pinned()) else None
+        ids, _ = self.batch_search_device(d_q, topk, ef, stream, device=dev, out=direct_out)
         if out is None:
             return ids.cpu().numpy().view(np.uint32)
-        out.copy_(ids)
-        if ids.is_cuda:
+        if direct_out is None:
+            out.copy_(ids)
+        if dev.type == "cuda":
             t.cuda.current_stream().synchronize()
         return out

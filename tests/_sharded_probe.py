@@ -32,6 +32,12 @@ for it in range(4):  # several steps: exercises the two buffer parities
         b_ids, b_dist = [t.clone() for t in nccl.batch_search_device(d_q, k, ef, stream.cuda_stream)]
         torch.cuda.synchronize()
         ok &= bool(torch.equal(a_ids, b_ids) and torch.equal(a_dist, b_dist))
+# host route: pinned buffers are used in place, pageable ones are copied; same answer either way
+qp = torch.from_numpy(q).pin_memory()
+outp = torch.full((nq, k), -1, dtype=torch.int32).pin_memory()
+peer.batch_search(qp, k, 64, out=outp, device=dev, stream=stream.cuda_stream)
+got_np = peer.batch_search(q, k, 64, device=dev, stream=stream.cuda_stream)
+ok &= bool(np.array_equal(outp.numpy(), a_ids.cpu().numpy()) and np.array_equal(got_np.view(np.int32), a_ids.cpu().numpy()))
 # every rank holds the same merged list
 g = [torch.empty_like(a_ids) for _ in range(world)]
 dist.all_gather(g, a_ids)
