@@ -26,7 +26,7 @@ SYMBOLS = [
     "ab_index_fit_spaces", "ab_index_set_graph", "ab_index_build_graph", "ab_index_graph_info", "ab_index_get_graph",
     "ab_index_get_codes", "ab_index_search_stats", "ab_index_batch_traverse", "ab_distance_pairs", "ab_quant_fit_encode",
     "ab_normalize_rows", "ab_bruteforce_topk", "ab_bruteforce_topk_device", "ab_merge_topk_device", "ab_last_error",
-    "ab_device_count", "ab_set_device", "ab_kernel_launch_count", "ab_version",
+    "ab_device_count", "ab_set_device", "ab_kernel_launch_count", "ab_version", "ab_debug_search_plan",
 ]
 
 
@@ -76,6 +76,15 @@ def _p(a, t):
 
 def _vp(x):
     return C.c_void_p(int(x)) if x is not None else C.c_void_p(0)
+
+
+def debug_search_plan(quant, row_chunks, ef, nq, n_rows, sm_count=148, smem_limit=232448):
+    """Host-side launch plan of the traversal (no device needed): dict of the six fields of ab_debug_search_plan."""
+    out = (C.c_uint64 * 6)()
+    check(lib().ab_debug_search_plan(C.c_int32(QUANTS[quant] if (quant is None or isinstance(quant, str)) else quant), C.c_uint32(row_chunks), C.c_uint32(ef),
+                                     C.c_uint64(nq), C.c_uint64(n_rows), C.c_int32(sm_count), C.c_uint64(smem_limit), out))
+    keys = ("warps_per_cta", "ctas_per_sm", "ctas", "hash_entries", "entry_bytes", "smem_per_cta")
+    return dict(zip(keys, [int(x) for x in out]))
 
 
 def kernel_launch_count() -> int:

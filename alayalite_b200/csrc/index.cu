@@ -522,6 +522,23 @@ int ab_index_batch_search_scatter_device(ab_index *index, const float *d_queries
   });
 }
 
+int ab_debug_search_plan(int32_t quant, uint32_t row_chunks, uint32_t ef, uint64_t nq, uint64_t n_rows, int32_t sm_count,
+                         uint64_t smem_limit, uint64_t out[6]) {
+  return guarded([&] {
+    AB_CHECK(out != nullptr && row_chunks >= 1 && ef >= 1 && sm_count >= 1 && smem_limit >= 48 * 1024, AB_ERR_INVALID,
+             "bad plan query");
+    const int table_len = quant == AB_QUANT_SQ8 ? row_chunks * 16 : (quant == AB_QUANT_SQ4 ? row_chunks * 32 : 0);
+    const SearchPlan p = plan_search(quant, static_cast<int>(row_chunks), table_len, 0.f, ef, static_cast<uint32_t>(nq),
+                                     static_cast<uint32_t>(n_rows), sm_count, smem_limit);
+    out[0] = p.warps_per_cta;
+    out[1] = p.ctas_per_sm;
+    out[2] = p.ctas;
+    out[3] = p.hash_size;
+    out[4] = p.hash_rbits != 0 ? 2 : 4;
+    out[5] = p.smem_bytes;
+  });
+}
+
 int ab_index_search_stats(ab_index *index, uint64_t stats[5]) {
   return guarded([&] {
     AB_CHECK(index != nullptr, AB_ERR_INVALID, "null index");

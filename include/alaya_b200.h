@@ -174,6 +174,14 @@ int ab_bruteforce_topk_device(int32_t metric, const float *d_data, uint64_t n, u
 int ab_merge_topk_device(const float *d_dist, const uint32_t *d_ids, uint32_t lists, uint64_t nq,
                          uint32_t k, uint32_t *d_out_ids, float *d_out_dist, void *stream);
 
+/* Launch plan the traversal would use (host-side decision only, no device needed): for quantization / row
+ * length in 16-byte chunks / ef / batch size / rows in the index on a device with `sm_count` SMs and
+ * `smem_limit` bytes of opt-in shared memory per block. out = {warps per CTA, resident CTAs per SM, CTAs,
+ * visited-table entries per warp, bytes per entry (2 = quotient entries, 4 = ids), dynamic shared memory per CTA}.
+ * Exposed so that the occupancy / carve-out policy is testable without a GPU. */
+int ab_debug_search_plan(int32_t quant, uint32_t row_chunks, uint32_t ef, uint64_t nq, uint64_t n_rows,
+                         int32_t sm_count, uint64_t smem_limit, uint64_t out[6]);
+
 /* Utilities */
 const char *ab_last_error(void);
 int ab_device_count(void);

@@ -93,3 +93,33 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower().replace("oracle/_ref", "").replace("the oracle", "") or f in ("synthetic.py",), f
+
+
+def test_search_plan_policy(cabi):
+    """Host-side launch plan: register-limited occupancy inside a 196 KB shared-memory carve-out where
+    possible, 16-bit visited entries when the id range allows, hash never below what the expected visited set needs."""
+    kb = 1024
+    p = cabi.debug_search_plan("none", 32, 52, 10_000, 1_000_000)
+    assert p["warps_per_cta"] * p["ctas_per_sm"] == 24 and p["entry_bytes"] == 2
+    assert p["ctas_per_sm"] * (p["smem_per_cta"] + kb) <= 196 * kb
+    assert p["hash_entries"] % 64 == 0 and p["hash_entries"] * 0.75 >= 24 * 52 * 1.25
+    assert p["ctas"] == 148 * p["ctas_per_sm"]
+    # small ef: quotient entries never go below 2048; few queries: no more CTAs than needed
+    assert cabi.debug_search_plan("none", 32, 10, 10_000, 1_000_000)["hash_entries"] == 2048
+    assert cabi.debug_search_plan("none", 32, 52, 100, 1_000_000)["ctas"] == 13
+    # ef 100 still fits 24 warps under 196 KB by tightening the table, not below 1.3 / 1.7 of the wanted size
+    p = cabi.debug_search_plan("none", 32, 100, 10_000, 1_000_000)
+    assert p["warps_per_cta"] * p["ctas_per_sm"] == 24 and p["hash_entries"] >= 24 * 1.3 * 100
+    assert p["ctas_per_sm"] * (p["smem_per_cta"] + kb) <= 196 * kb
+    # id range too large for (displacement, remainder) in 16 bits: plain 32-bit ids
+    assert cabi.debug_search_plan("none", 24, 40, 10_000, 12_500_000)["entry_bytes"] == 4
+    # quantised spaces run the 128-register kernels: two CTAs of 8 warps
+    for quant, chunks in (("sq8", 60), ("sq4", 24)):
+        p = cabi.debug_search_plan(quant, chunks, 100, 10_000, 500_000)
+        assert p["warps_per_cta"] * p["ctas_per_sm"] <= 16 and p["entry_bytes"] == 2
+    # very large ef: at least 10 warps stay resident and the plan always fits the device limit
+    for ef, floor in ((200, 10), (400, 10), (1000, 10), (4096, 4)):  # the pool itself is 8 B x ef per warp
+        p = cabi.debug_search_plan("none", 32, ef, 10_000, 1_000_000)
+        assert p["warps_per_cta"] * p["ctas_per_sm"] >= floor and p["smem_per_cta"] + kb <= 227 * kb, (ef, p)
+    with pytest.raises(Exception):
+        cabi.debug_search_plan("none", 0, 52, 10, 10)
