@@ -296,13 +296,19 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
             for (int g = 0; g < 4; g++) {
               if (m4[g] <= thr) {
+                // branch-free mask of the passing columns (independent compares), then one append per set bit
+                const float4 sa = *reinterpret_cast<const float4 *>(sxb + cc + g * 8);
+                const float4 sb = *reinterpret_cast<const float4 *>(sxb + cc + g * 8 + 4);
+                const float sx8[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                uint32_t pass = 0;
 #pragma unroll
-                for (int j = g * 8; j < g * 8 + 8; j++) {
-                  const float s = fmaf(a.alpha, __uint_as_float(v[h][j]), sxb[cc + j]);
-                  if (s <= thr) {
-                    const uint32_t pos = atomicAdd(&scnt[row], 1u);
-                    if (pos < a.cap) my[pos] = static_cast<uint32_t>(r0 + cc + j);
-                  }
+                for (int j = 0; j < 8; j++)
+                  pass |= (fmaf(a.alpha, __uint_as_float(v[h][g * 8 + j]), sx8[j]) <= thr ? 1u : 0u) << j;
+                while (pass) {
+                  const int j = __ffs(pass) - 1;
+                  pass &= pass - 1;
+                  const uint32_t pos = atomicAdd(&scnt[row], 1u);
+                  if (pos < a.cap) my[pos] = static_cast<uint32_t>(r0 + cc + g * 8 + j);
                 }
               }
             }
