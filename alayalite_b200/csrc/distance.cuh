@@ -180,18 +180,9 @@ struct U64x2 {
 };
 __device__ __forceinline__ U64x2 ldg128_pairs(const void *p) {
   U64x2 r;
-#ifndef AB_LOADMODE
-#define AB_LOADMODE 0
-#endif
-#if AB_LOADMODE == 0
+  // plain non-coherent load: measured against L1::no_allocate, ld.global.cg and L1::evict_first on the bench
+  // workload (r01: no_allocate -4 %, evict_first -10 %, cg +-0)
   asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
-#elif AB_LOADMODE == 1
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
-#elif AB_LOADMODE == 2
-  asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
-#else
-  asm volatile("ld.global.nc.L1::evict_first.v2.u64 {%0,%1}, [%2];" : "=l"(r.a), "=l"(r.b) : "l"(p));
-#endif
   return r;
 }
 __device__ __forceinline__ unsigned long long f2sub(unsigned long long x, unsigned long long y) {

@@ -264,9 +264,8 @@ __device__ __forceinline__ float multi_distance(const uint8_t *r0, const uint8_t
   }
 }
 
-#ifndef AB_HASH_FACTOR
-#define AB_HASH_FACTOR 1.34f
-#endif
+// candidates per lane group kept in flight by the multi-candidate path, and resident CTAs the raw kernels are
+// built for (compile-time experiment knobs, see scripts/build_variant.sh)
 #ifndef AB_INFLIGHT
 #define AB_INFLIGHT 3
 #endif
