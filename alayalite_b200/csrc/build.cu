@@ -316,7 +316,7 @@ void build_layer(ab_index *ix, const LayerJob &job, uint32_t efc, uint32_t max_b
     const uint32_t *batch_ids = job.d_sequence + inserted;
 
     // 1. candidates: the query traversal kernel at ef_construction over the graph built so far
-    SearchPlan plan = plan_search(AB_QUANT_NONE, job.view.nchunks, 0, 0.f, efc, B, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
+    SearchPlan plan = plan_search(AB_QUANT_NONE, job.view.nchunks, 0, 1.2f, efc, B, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
     if (w.slots < plan.slots) throw Error(AB_ERR_INVALID, "build workspace: bitmap slots");
     AB_CUDA(cudaMemsetAsync(w.counter.p, 0, sizeof(uint32_t), s));
     SearchArgs a{};
@@ -442,7 +442,7 @@ void index_build_graph(ab_index *ix, uint32_t ef_construction) {
   AB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, w.edge_dst.p, w.sorted_dst.p, w.idx.p, w.sorted_idx.p,
                                           static_cast<int>(max_edges), 0, 32, s));
   w.cub_tmp.reserve(w.cub_bytes + 16);
-  SearchPlan big = plan_search(AB_QUANT_NONE, ix->raw_chunks, 0, 0.f, efc, max_batch, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
+  SearchPlan big = plan_search(AB_QUANT_NONE, ix->raw_chunks, 0, 1.2f, efc, max_batch, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
   w.bitmap_words = round_up((size_t(n) + 31) / 32, 4);
   w.slots = big.slots;
   w.bitmaps.alloc_zero(w.bitmap_words * w.slots, s);

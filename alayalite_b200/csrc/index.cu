@@ -299,7 +299,8 @@ static void search_host(ab_index *ix, const float *queries, uint64_t nq, uint32_
   AB_CUDA(cudaStreamSynchronize(s));
   for (int i = 0; i < 4; i++) ix->last_stats[i] = st[i];
   ix->last_stats[4] = nq;
-  if (nq >= 32 && ix->last_ef > 0) ix->visit_ratio = static_cast<float>(double(st[0]) / double(nq) / double(ix->last_ef));
+  if (nq >= 32 && ix->last_ef > 0)
+    ix->visit_ratio = static_cast<float>(double(st[0]) / double(nq) / double(ix->last_ef)) / visited_model(ix->last_ef);
 }
 
 }  // namespace ab

@@ -63,7 +63,7 @@ struct ab_index {
   int bitmap_slots = 0;
   uint64_t last_stats[5] = {0, 0, 0, 0, 0};
   uint32_t last_ef = 0;      // ef of the launch the device counters belong to
-  float visit_ratio = 0.f;   // visited ids per query / ef, from the last counters read back (sizes the visited hash)
+  float visit_ratio = 0.f;   // visited ids per query / ef over visited_model(ef), from the last counters read back
 };
 
 namespace ab {

@@ -149,6 +149,8 @@ void launch_search_raw(const SearchPlan &p, const SearchArgs &a, cudaStream_t s)
 
 }  // namespace
 
+float visited_model(uint32_t ef) { return 16.0f + 400.0f / static_cast<float>(std::max(1u, ef)); }
+
 SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
                        int sm_count, size_t smem_limit) {
   SearchPlan p{};
@@ -156,10 +158,11 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   static const float hash_factor = getenv("AB_HASH_FACTOR") ? static_cast<float>(atof(getenv("AB_HASH_FACTOR"))) : 1.7f;
   static const int max_warps = getenv("AB_MAX_WARPS") ? atoi(getenv("AB_MAX_WARPS")) : 64;
   static const int hash16 = getenv("AB_HASH16") ? atoi(getenv("AB_HASH16")) : 1;
-  // Hash entries per warp so that nearly every query stays below the 3/4 spill mark: visited ids per query
-  // grow like ratio * ef, ratio ~ 21-24 on SIFT-like graphs and higher on harder data (taken from earlier
-  // searches of this index); 1.7 = 1 / 0.75 load x 1.28 for the spread between queries.
-  const float ratio = std::max(24.0f, visit_ratio);
+  // Hash entries per warp so that nearly every query stays below the 3/4 spill mark. Visited ids per query grow
+  // like ratio(ef) * ef with ratio(ef) ~ 16 + 400 / ef on SIFT-like graphs (31 at ef 20, 23.6 at ef 52, 20.9 at ef 100,
+  // 18.7 at ef 200, measured); visit_ratio is this index's own measured multiple of that model (0 = unknown, 1.0
+  // assumed; harder data has more). 1.7 = 1 / 0.75 load x 1.28 for the spread between queries.
+  const float ratio = visited_model(ef) * (visit_ratio > 0.f ? std::min(4.0f, std::max(0.75f, visit_ratio)) : 1.0f);
   uint32_t h = static_cast<uint32_t>(ratio * hash_factor * static_cast<float>(ef));
   h = std::min(32768u, std::max(512u, (h + 63u) & ~63u));
   const size_t cta_fixed = quant != AB_QUANT_NONE ? size_t(table_len) * 8 : 0;

@@ -93,7 +93,10 @@ struct SearchPlan {
   int slots;          // ctas * warps_per_cta (bitmap slots needed)
 };
 
-// visit_ratio: visited ids per query divided by ef, measured on earlier searches of this index (0 = unknown)
+// expected visited ids per query divided by ef on SIFT-like graphs
+float visited_model(uint32_t ef);
+// visit_ratio: visited ids per query / ef measured on earlier searches of this index, as a multiple of
+// visited_model(ef) at the ef it was measured with (0 = unknown)
 SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
                        int sm_count, size_t smem_limit);
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
