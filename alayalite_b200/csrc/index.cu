@@ -176,6 +176,26 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   }
   ix->w_counter.reserve(1);
   ix->w_stats.reserve(4);
+  // feedback from earlier launches (visited ids per query size the visited table), without blocking the stream
+  if (ix->stats_pending && cudaEventQuery(ix->stats_event) == cudaSuccess) {
+    ix->stats_pending = false;
+    if (ix->stats_nq >= 32 && ix->stats_ef > 0)
+      ix->visit_ratio = static_cast<float>(double(ix->h_stats[0]) / double(ix->stats_nq) / double(ix->stats_ef)) /
+                        visited_model(ix->stats_ef);
+  }
+  cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+  // one measurement per ef value is enough: a steady loop at one ef pays for the copy once
+  if (!ix->stats_pending && ix->last_ef > 0 && ix->last_nq >= 32 && ix->last_ef != ix->stats_ef) {
+    if (ix->h_stats == nullptr) {
+      AB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ix->h_stats), 4 * sizeof(unsigned long long)));
+      AB_CUDA(cudaEventCreateWithFlags(&ix->stats_event, cudaEventDisableTiming));
+    }
+    AB_CUDA(cudaMemcpyAsync(ix->h_stats, ix->w_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    AB_CUDA(cudaEventRecord(ix->stats_event, stream));
+    ix->stats_pending = true;
+    ix->stats_ef = ix->last_ef;
+    ix->stats_nq = ix->last_nq;
+  }
   AB_CUDA(cudaMemsetAsync(ix->w_counter.p, 0, sizeof(uint32_t), stream));
   AB_CUDA(cudaMemsetAsync(ix->w_stats.p, 0, 4 * sizeof(unsigned long long), stream));
 
@@ -220,6 +240,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   if (scatter != nullptr && !need_rerank) a.scatter = *scatter;
   launch_search(quant, plan, a, stream);
   ix->last_ef = ef;
+  ix->last_nq = nq;
 
   if (need_rerank) {
     RerankArgs r{};
@@ -363,6 +384,11 @@ void ab_index_destroy(ab_index *index) {
     cudaStreamSynchronize(index->stream);
     cudaStreamDestroy(index->stream);
   }
+  if (index->stats_event) {
+    cudaEventSynchronize(index->stats_event);
+    cudaEventDestroy(index->stats_event);
+  }
+  if (index->h_stats) cudaFreeHost(index->h_stats);
   delete index;
 }
 

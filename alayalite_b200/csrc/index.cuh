@@ -63,6 +63,14 @@ struct ab_index {
   int bitmap_slots = 0;
   uint64_t last_stats[5] = {0, 0, 0, 0, 0};
   uint32_t last_ef = 0;      // ef of the launch the device counters belong to
+  uint64_t last_nq = 0;      // and its query count
+  // lag-free feedback for device-resident callers (no synchronisation on their stream): the counters of launch k
+  // are copied to pinned host memory at the start of launch k+1 and picked up once that copy's event has fired
+  unsigned long long *h_stats = nullptr;  // pinned [4]
+  cudaEvent_t stats_event = nullptr;
+  bool stats_pending = false;
+  uint32_t stats_ef = 0;
+  uint64_t stats_nq = 0;
   float visit_ratio = 0.f;   // visited ids per query / ef over visited_model(ef), from the last counters read back
 };
 
