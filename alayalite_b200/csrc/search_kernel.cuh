@@ -183,6 +183,58 @@ __device__ __forceinline__ void pool_insert(uint2 *pool, int &size, int &cur, in
   }
 }
 
+// All accepted candidates of one hop at once (ef <= 64: two pool entries per lane). Equivalent to inserting them
+// one by one in neighbour order: a candidate lands behind the pool entries with distance <= its own and behind
+// the accepted candidates that precede it (smaller distance, or equal distance and earlier neighbour slot);
+// a pool entry moves right by the number of candidates strictly closer than it; whatever ends at index >= ef is
+// dropped (the sequential insert would have evicted or rejected it). `accept` / `d` / `v` are per lane, `acc` the
+// ballot of `accept`, `sel` the lane whose candidate is the next hop (inserted with its expanded flag) or -1.
+// The cursor follows the first un-expanded entry: the old cursor entry at its new index, or an inserted one.
+__device__ __forceinline__ void pool_merge(uint2 *pool, const float *cdist, uint32_t newmask, int &size, int &cur, int ef,
+                                           uint32_t acc, int sel, bool accept, float d, uint32_t v, int lane) {
+  const bool two = size > 32;  // warp-uniform
+  const bool valid0 = lane < size, valid1 = two && lane + 32 < size;
+  uint2 e0 = make_uint2(0u, 0u), e1 = make_uint2(0u, 0u);
+  if (valid0) e0 = pool[lane];
+  if (valid1) e1 = pool[lane + 32];
+  const float d0 = __uint_as_float(e0.x), d1 = __uint_as_float(e1.x);
+  int shift0 = 0, shift1 = 0, mypos = 0, before = 0;
+  const int nacc = __popc(acc);
+  for (uint32_t rest = acc; rest;) {
+    const int j = __ffs(rest) - 1;
+    rest &= rest - 1;
+    const float dj = cdist[__popc(newmask & ((1u << j) - 1))];  // uniform shared-memory read
+    shift0 += (valid0 && dj < d0) ? 1 : 0;
+    int le = __popc(__ballot_sync(kFull, valid0 && d0 <= dj));
+    if (two) {
+      shift1 += (valid1 && dj < d1) ? 1 : 0;
+      le += __popc(__ballot_sync(kFull, valid1 && d1 <= dj));
+    }
+    if (lane == j) mypos = le;
+    before += (accept && lane != j && (dj < d || (dj == d && j < lane))) ? 1 : 0;
+  }
+  mypos += before;
+  const int n0 = lane + shift0, n1 = lane + 32 + shift1;
+  // cursor: new index of the entry it pointed at (if it survives), else the end; then any un-expanded insert before it
+  int c = size;
+  if (cur < size) {
+    const int sh = __shfl_sync(kFull, cur >= 32 ? shift1 : shift0, cur & 31);
+    c = cur + sh;
+  } else {
+    c = size + nacc;
+  }
+  const int nsize = min(size + nacc, ef);
+  const int ins = (accept && lane != sel && mypos < ef) ? mypos : 0x7FFFFFFF;
+  c = min(min(c, nsize), static_cast<int>(__reduce_min_sync(kFull, static_cast<unsigned>(ins))));
+  __syncwarp();
+  if (valid0 && n0 < ef) pool[n0] = e0;
+  if (valid1 && n1 < ef) pool[n1] = e1;
+  if (accept && mypos < ef) pool[mypos] = make_uint2(__float_as_uint(d), lane == sel ? (v | kCheckedBit) : v);
+  __syncwarp();
+  size = nsize;
+  cur = c;
+}
+
 // order-preserving map float -> uint32 (for warp-wide integer min)
 __device__ __forceinline__ uint32_t float_key(float f) {
   const uint32_t b = __float_as_uint(f);
@@ -550,7 +602,11 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       }
       const uint32_t v_next = a.adj[size_t(u) * kR + lane];
 
-      // inserts in neighbour order
+      // inserts in neighbour order: one merge step when the pool fits two entries per lane, else one by one
+      if (ef <= 64) {
+        if (acc) pool_merge(ws.pool, ws.cdist, newmask, size, cur, ef, acc, sel, accept, d, v, lane);
+        acc = 0;
+      }
       while (acc) {
         const int j = __ffs(acc) - 1;
         acc &= acc - 1;
