@@ -111,7 +111,10 @@ class NativeIndex:
 
     def __del__(self):
         if getattr(self, "_own", False) and getattr(self, "h", None):
-            lib().ab_index_destroy(self.h)
+            try:
+                lib().ab_index_destroy(self.h)
+            except TypeError:  # interpreter shutdown: module globals are already gone
+                pass
             self.h = None
 
     @property

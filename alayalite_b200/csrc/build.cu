@@ -445,7 +445,7 @@ void index_build_graph(ab_index *ix, uint32_t ef_construction) {
   SearchPlan big = plan_search(AB_QUANT_NONE, ix->raw_chunks, 0, 1.2f, efc, max_batch, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
   w.bitmap_words = round_up((size_t(n) + 31) / 32, 4);
   w.slots = big.slots;
-  w.bitmaps.alloc_zero(w.bitmap_words * w.slots, s);
+  w.bitmaps.alloc_zero((w.bitmap_words + kSpillList) * w.slots, s);
 
   // ---- upper layers, top down, in a compact id space (position in `order`) ------------------------
   const uint32_t m1 = maxlevel >= 1 ? cnt[1] : 0;

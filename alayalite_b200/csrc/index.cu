@@ -170,7 +170,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   // private visited bitmaps, one per resident warp, all-zero between launches
   const size_t words = round_up((std::max<uint64_t>(ix->capacity, ix->n) + 31) / 32, 4);
   if (ix->bitmap_words != words || ix->bitmap_slots < plan.slots) {
-    ix->w_bitmaps.alloc_zero(words * plan.slots, stream);
+    ix->w_bitmaps.alloc_zero((words + kSpillList) * plan.slots, stream);
     ix->bitmap_words = words;
     ix->bitmap_slots = plan.slots;
   }

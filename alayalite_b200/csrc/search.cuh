@@ -9,6 +9,7 @@ namespace ab {
 // results (ids + id_offset) are stored straight into the [slots, nq, topk] gather buffers of every rank of
 // the box -- peer memory mapped over NVLink -- at slot `slot`, so the transfer overlaps the search.
 constexpr int kMaxDest = 16;
+constexpr uint32_t kSpillList = 4096;  // ids remembered per query for the targeted bitmap clean-up
 struct Scatter {
   int n_dest;  // 0 = off
   uint32_t slot;
@@ -59,7 +60,10 @@ struct SearchArgs {
   int hash_xshift;              // 32 - bits of the id space
   uint32_t hash_rmul;           // remainder = umulhi(low word of scramble * entries, hash_rmul)
   uint32_t hash_dlimit;         // first invalid entry code (displacement range exhausted)
-  uint32_t *bitmaps;            // [slots, bitmap_words] all zero between launches
+  // per-warp visited bitmaps: [slots, bitmap_words + kSpillList] words. The first bitmap_words of a slot are the
+  // bitmap (all zero between launches); the tail is a scratch list of the ids a query put there, so that giving
+  // the bitmap back clean costs a few hundred word stores instead of rewriting N / 8 bytes
+  uint32_t *bitmaps;
   size_t bitmap_words;
   unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, spilled queries}
 };

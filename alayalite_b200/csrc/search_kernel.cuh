@@ -29,15 +29,18 @@ struct Visited {
   uint32_t *hash;
   bool spilled;      // the hash is frozen, new ids go to the bitmap
   bool bitmap_used;  // the warp's global bitmap holds bits and must be cleared after the query
+  uint32_t listed;   // ids this query set in the bitmap (the first kSpillList of them are in the slot's list)
 };
 
 // multiply-shift range reduction: any table size, no power-of-two rounding of the shared-memory footprint
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t size) { return __umulhi(key * 0x9E3779B1u, size); }
 
+__device__ __forceinline__ uint32_t *bitmap_slot(const SearchArgs &a) {
+  return a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (a.bitmap_words + kSpillList);
+}
 __device__ __forceinline__ bool bitmap_test_and_set(const SearchArgs &a, uint32_t key) {
-  uint32_t *bitmap = a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * a.bitmap_words;
   const uint32_t bit = 1u << (key & 31);
-  return (atomicOr(&bitmap[key >> 5], bit) & bit) == 0;
+  return (atomicOr(&bitmap_slot(a)[key >> 5], bit) & bit) == 0;
 }
 
 // Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
@@ -115,7 +118,14 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
     }
   }
   if (__any_sync(kFull, to_bitmap)) {
-    if (to_bitmap) is_new = bitmap_test_and_set(a, key);
+    bool added = false;
+    if (to_bitmap) added = is_new = bitmap_test_and_set(a, key);
+    const uint32_t am = __ballot_sync(kFull, added);
+    if (added) {  // remember the id for the clean-up
+      const uint32_t pos = vs.listed + __popc(am & ((1u << (threadIdx.x & 31)) - 1));
+      if (pos < kSpillList) bitmap_slot(a)[a.bitmap_words + pos] = key;
+    }
+    vs.listed += __popc(am);
     vs.bitmap_used = true;
     __syncwarp();
   }
@@ -475,6 +485,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     uint32_t ndc = 0, hops = 0, ndc_ov = 0;  // per query: far below 2^32
     vs.spilled = false;
     vs.bitmap_used = false;
+    vs.listed = 0;
 
     // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
     uint32_t u = a.ep;
@@ -642,9 +653,16 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       if (lane == 0) a.pool_sizes[qi] = size;
     }
     if (vs.bitmap_used) {
-      // give the private bitmap back all-zero (the reference allocates + zeroes one per query)
-      uint4 *bm = reinterpret_cast<uint4 *>(a.bitmaps + size_t(blockIdx.x * warps + warp) * a.bitmap_words);
-      for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
+      // give the private bitmap back all-zero (the reference allocates + zeroes one per query): only the words of
+      // the listed ids, or the whole bitmap if the list overflowed
+      uint32_t *bmw = bitmap_slot(a);
+      __syncwarp();
+      if (vs.listed <= kSpillList) {
+        for (uint32_t i = lane; i < vs.listed; i += 32) bmw[bmw[a.bitmap_words + i] >> 5] = 0u;
+      } else {
+        uint4 *bm = reinterpret_cast<uint4 *>(bmw);
+        for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
+      }
     }
     if (lane == 0) {
       atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
