@@ -8,20 +8,9 @@
 //   Scheduler / Worker coroutine executor  include/executor/scheduler.hpp:113-203, worker.hpp:111-136
 //   PyIndex::rerank                        python/include/index.hpp:450-488
 //
-// Design. One warp owns one query at a time and pulls the next query index from a global counter
-// (the role of the reference's task queue). Per hop the warp
-//   1. pops the closest un-expanded pool entry (pool lives in shared memory, sorted, expanded flag
-//      in bit 31 of the id exactly like LinearPool),
-//   2. reads the 128-byte adjacency row with one coalesced load (lane j <- neighbour j),
-//   3. filters neighbours through the visited set: an exact open-addressing hash of ids in shared
-//      memory; when a query outgrows it, the warp spills to its private N-bit bitmap in global
-//      memory (the reference's structure) -- never a false "visited", never a false "new",
-//   4. evaluates all unvisited neighbours: sub-warps of TPV lanes each stream one candidate row with
-//      128-bit loads, up to MAXC loads in flight per lane, dequantisation fused (distance.cuh),
-//   5. inserts candidates in neighbour order with the reference's rule (reject if full and
-//      d >= worst; position = upper bound; cursor moves back if the insert lands before it).
-// Distances are plain fp32; given equal distance values the traversal is step-for-step the
-// reference's, so ids are identical up to fp32 summation-order effects.
+// This file: the re-rank kernel, the launch plan (occupancy / shared-memory carve-out / visited-table format) and
+// the dispatch of the raw-row kernel variants. The traversal kernel itself is in search_kernel.cuh (design notes
+// there and in DESIGN.md 4.1); its SQ instantiations are in search_sq8.cu / search_sq4.cu.
 #include "search_kernel.cuh"
 
 namespace ab {

@@ -1,5 +1,20 @@
 // Device code of the traversal kernel + its launcher, shared by the translation units that instantiate it
 // (search.cu: raw rows; search_sq8.cu / search_sq4.cu: quantised spaces) so that they compile in parallel.
+//
+// Design. One warp owns one query at a time and pulls the next query index from a global counter (the role of the
+// reference's task queue). Per hop the warp
+//   1. holds the 128-byte adjacency row of the node being expanded (one coalesced load, lane j <- neighbour j),
+//   2. filters the neighbours through the visited set: an exact open-addressing table in shared memory (16-bit
+//      quotient entries or 32-bit ids, vote-driven probe loop); a query that outgrows it continues in the warp's
+//      private N-bit bitmap in global memory (the reference's structure) -- never a false "visited" or "new",
+//   3. evaluates all unvisited neighbours: sub-warps of TPV lanes per candidate row, 128-bit loads, three candidates
+//      per sub-warp in flight, query chunks read from shared memory after the loads are issued, packed f32x2 math,
+//      dequantisation fused for SQ codes (distance.cuh),
+//   4. determines the next node to expand from the pool and the fresh distances and requests its adjacency row,
+//   5. merges the accepted candidates into the sorted pool (LinearPool semantics: reject if full and d >= worst,
+//      position = upper bound, cursor = first un-expanded entry) while that load is in flight.
+// Distances are plain fp32; given equal distance values the traversal is step-for-step the reference's, so ids are
+// identical up to fp32 summation-order effects (bit-identical on integer-valued data).
 #pragma once
 #include <cfloat>
 #include <cstdlib>
