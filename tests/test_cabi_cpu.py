@@ -111,8 +111,9 @@ def test_search_plan_policy(cabi):
     p = cabi.debug_search_plan("none", 32, 100, 10_000, 1_000_000)
     assert p["warps_per_cta"] * p["ctas_per_sm"] == 24 and p["hash_entries"] >= 24 * 1.3 * 100
     assert p["ctas_per_sm"] * (p["smem_per_cta"] + kb) <= 196 * kb
-    # id range too large for (displacement, remainder) in 16 bits: plain 32-bit ids
-    assert cabi.debug_search_plan("none", 24, 40, 10_000, 12_500_000)["entry_bytes"] == 4
+    # quotient entries as long as two displacement bits remain (12.5 M rows: 14 + 2 bits); beyond that plain 32-bit ids
+    assert cabi.debug_search_plan("none", 24, 40, 10_000, 12_500_000)["entry_bytes"] == 2
+    assert cabi.debug_search_plan("none", 24, 40, 10_000, 100_000_000)["entry_bytes"] == 4
     # quantised spaces run the 128-register kernels: two CTAs of 8 warps
     for quant, chunks in (("sq8", 60), ("sq4", 24)):
         p = cabi.debug_search_plan(quant, chunks, 100, 10_000, 500_000)

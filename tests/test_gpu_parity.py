@@ -327,17 +327,19 @@ def test_visited_table_formats_agree(cabi, tmp_path):
     probe = os.path.join(os.path.dirname(__file__), "_visited_probe.py")
     runs = {}
     for name, env in {"default": {}, "ids32": {"AB_HASH16": "0"}, "tiny16": {"AB_HASH_FACTOR": "0.05"},
-                      "tiny32": {"AB_HASH16": "0", "AB_HASH_FACTOR": "0.05"}}.items():
+                      "tiny32": {"AB_HASH16": "0", "AB_HASH_FACTOR": "0.05"},
+                      "nodisp": {"AB_HASH_DBITS_CAP": "1"}}.items():  # home slot only: most probes end in the bitmap
         out = str(tmp_path / f"{name}.npz")
         r = subprocess.run([sys.executable, probe, str(folder), out, "16", "64", "300"], env={**os.environ, **env},
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         runs[name] = np.load(out)
     for ef in (16, 64, 300):
-        for name in ("ids32", "tiny16", "tiny32"):
+        for name in ("ids32", "tiny16", "tiny32", "nodisp"):
             assert np.array_equal(runs[name][f"ids{ef}"], runs["default"][f"ids{ef}"]), (name, ef)
             assert np.array_equal(runs[name][f"dist{ef}"], runs["default"][f"dist{ef}"]), (name, ef)
     assert int(runs["tiny16"]["bitmap300"]) > 0 and int(runs["tiny32"]["bitmap300"]) > 0
+    assert int(runs["nodisp"]["bitmap64"]) > 0
     assert int(runs["default"]["bitmap64"]) == 0
 
 
