@@ -56,6 +56,16 @@ ci, cd = torch.cat(gi, 1).cpu().numpy().astype(np.int64), torch.cat(gd, 1).cpu()
 order = np.lexsort((ci, cd), axis=1)[:, :k]
 want = np.take_along_axis(ci, order, 1)
 ok &= bool(np.array_equal(want, a_ids.cpu().numpy().astype(np.int64)))
+# quantised space: the final lists come from the re-rank kernel, which carries the peer stores there
+ix8 = _cabi.NativeIndex("l2", "sq8", n)
+ix8.fit(base, 80)
+peer8 = ShardedIndex(ix8, rank * n, world, peer_memory=True)
+nccl8 = ShardedIndex(ix8, rank * n, world, peer_memory=False)
+for ef in (32, 100):
+    p_ids, p_dist = [t.clone() for t in peer8.batch_search_device(d_q, k, ef, stream.cuda_stream)]
+    c_ids, c_dist = [t.clone() for t in nccl8.batch_search_device(d_q, k, ef, stream.cuda_stream)]
+    torch.cuda.synchronize()
+    ok &= bool(torch.equal(p_ids, c_ids) and torch.equal(p_dist, c_dist))
 print(f"rank {rank} ok={ok} exchange={peer.exchange_kind!r} err={getattr(peer, 'peer_error', None)}", flush=True)
 flag = torch.tensor([int(ok and peer.exchange_kind.startswith('peer'))], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
