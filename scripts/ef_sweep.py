@@ -9,10 +9,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1_000_000); ap.add_argument("--dim", type=int, default=128)
 ap.add_argument("--quant", default="none"); ap.add_argument("--metric", default="l2")
 ap.add_argument("--latent", type=int, default=16); ap.add_argument("--topk", type=int, default=10)
+ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("efs", nargs="*", type=int)
 a = ap.parse_args()
 efs = a.efs or [20, 52, 100]
-n, dim, nq, k = a.n, a.dim, 10_000, a.topk
+n, dim, nq, k = a.n, a.dim, a.nq, a.topk
 base, q = low_rank(n, dim, nq, a.latent, seed=42, normalize=(a.metric != "l2"))
 ix = _cabi.NativeIndex(a.metric, a.quant, n)
 t = time.time(); ix.fit(base, 100); print(f"fit {time.time()-t:.2f}s", flush=True)
