@@ -22,9 +22,10 @@ SYMBOLS = [
     "ab_index_create", "ab_index_destroy", "ab_index_fit", "ab_index_search", "ab_index_batch_search",
     "ab_index_batch_search_with_distance", "ab_index_insert", "ab_index_remove", "ab_index_get_data_by_id",
     "ab_index_get_dim", "ab_index_get_size", "ab_index_save", "ab_index_load", "ab_index_batch_search_device",
-    "ab_index_batch_search_scatter_device",
+    "ab_quant_minmax", "ab_index_fit_ranged", "ab_group_create", "ab_group_destroy", "ab_group_fit", "ab_group_batch_search",
+    "ab_group_index", "ab_comm_create", "ab_comm_connect", "ab_comm_batch_search_device", "ab_comm_errors", "ab_comm_destroy",
     "ab_index_fit_spaces", "ab_index_set_graph", "ab_index_build_graph", "ab_index_graph_info", "ab_index_get_graph",
-    "ab_index_get_codes", "ab_index_search_stats", "ab_index_batch_traverse", "ab_distance_pairs", "ab_quant_fit_encode",
+    "ab_index_get_codes", "ab_index_search_stats", "ab_index_search_stats_ex", "ab_index_batch_traverse", "ab_distance_pairs", "ab_quant_fit_encode",
     "ab_normalize_rows", "ab_bruteforce_topk", "ab_bruteforce_topk_device", "ab_merge_topk_device", "ab_last_error",
     "ab_device_count", "ab_set_device", "ab_kernel_launch_count", "ab_version", "ab_debug_search_plan",
 ]
@@ -132,6 +133,10 @@ class NativeIndex:
         d = _f32(data)
         check(lib().ab_index_fit(self.h, _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]), C.c_uint32(ef_construction), C.c_uint32(num_threads)))
 
+    def fit_ptr(self, ptr, n, dim, ef_construction=100):
+        """Rows behind a raw pointer: host memory, or device memory on the index's device (staged in place)."""
+        check(lib().ab_index_fit(self.h, C.cast(_vp(ptr), f32p), C.c_uint64(n), C.c_uint32(dim), C.c_uint32(ef_construction), C.c_uint32(1)))
+
     def fit_spaces(self, data):
         d = _f32(data)
         check(lib().ab_index_fit_spaces(self.h, _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1])))
@@ -217,9 +222,10 @@ class NativeIndex:
         return ids, dist, sizes
 
     def stats(self):
-        st = (C.c_uint64 * 5)()
-        check(lib().ab_index_search_stats(self.h, st))
-        return dict(ndc=int(st[0]), hops=int(st[1]), overlay=int(st[2]), spilled=int(st[3]), queries=int(st[4]))
+        st = (C.c_uint64 * 8)()
+        check(lib().ab_index_search_stats_ex(self.h, st, C.c_uint32(8)))
+        return dict(ndc=int(st[0]), hops=int(st[1]), overlay=int(st[2]), spilled=int(st[3]), queries=int(st[4]),
+                    bitmap=int(st[5]), overflow_ids=int(st[6]), visited_workspace_bytes=int(st[7]))
 
     def insert(self, vec, ef=100):
         v = _f32(vec)

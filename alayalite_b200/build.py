@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libalaya_b200.so")
 PYMOD = os.path.join(HERE, "_alayalitepy" + sysconfig.get_config_var("EXT_SUFFIX"))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CU_SOURCES = ["index.cu", "search.cu", "search_sq8.cu", "search_sq4.cu", "quant.cu", "bruteforce.cu", "bruteforce_tc.cu", "io.cu", "build.cu", "update.cu"]
+CU_SOURCES = ["index.cu", "search.cu", "search_sq8.cu", "search_sq4.cu", "quant.cu", "bruteforce.cu", "bruteforce_tc.cu", "io.cu", "build.cu", "update.cu", "group.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

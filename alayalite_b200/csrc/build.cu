@@ -232,13 +232,12 @@ __global__ void export_overlay_kernel(const uint32_t *__restrict__ ladj, uint32_
 }
 
 struct Workspace {
-  DevBuf<uint32_t> pool_ids, pool_sizes, first, edge_dst, edge_src, sorted_dst, idx, sorted_idx, counter, bitmaps;
+  DevBuf<uint32_t> pool_ids, pool_sizes, first, edge_dst, edge_src, sorted_dst, idx, sorted_idx, counter;
   DevBuf<float> pool_dist, edge_dist;
   DevBuf<unsigned long long> stats;
   DevBuf<uint8_t> cub_tmp;
   size_t cub_bytes = 0;
-  size_t bitmap_words = 0;
-  int slots = 0;
+  VisitedWorkspace visited;
 };
 
 int pick_build_tpv(int nchunks) {
@@ -317,7 +316,7 @@ void build_layer(ab_index *ix, const LayerJob &job, uint32_t efc, uint32_t max_b
 
     // 1. candidates: the query traversal kernel at ef_construction over the graph built so far
     SearchPlan plan = plan_search(AB_QUANT_NONE, job.view.nchunks, 0, 1.2f, efc, B, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
-    if (w.slots < plan.slots) throw Error(AB_ERR_INVALID, "build workspace: bitmap slots");
+    w.visited.prepare(plan, ix->n, s);
     AB_CUDA(cudaMemsetAsync(w.counter.p, 0, sizeof(uint32_t), s));
     SearchArgs a{};
     a.rows = job.view.rows;
@@ -346,8 +345,7 @@ void build_layer(ab_index *ix, const LayerJob &job, uint32_t efc, uint32_t max_b
     a.pool_sizes = w.pool_sizes.p;
     a.work_counter = w.counter.p;
     a.hash_size = plan.hash_size;
-    a.bitmaps = w.bitmaps.p;
-    a.bitmap_words = w.bitmap_words;
+    w.visited.fill(a);
     a.stats = w.stats.p;
     launch_search(AB_QUANT_NONE, plan, a, s);
 
@@ -434,8 +432,8 @@ void index_build_graph(ab_index *ix, uint32_t ef_construction) {
   w.idx.reserve(max_edges);
   w.sorted_idx.reserve(max_edges);
   w.counter.reserve(1);
-  w.stats.reserve(4);
-  AB_CUDA(cudaMemsetAsync(w.stats.p, 0, 32, s));
+  w.stats.reserve(8);
+  AB_CUDA(cudaMemsetAsync(w.stats.p, 0, 64, s));
   iota_kernel<<<(max_edges + 255) / 256, 256, 0, s>>>(w.idx.p, max_edges);
   AB_CUDA(cudaGetLastError());
   count_launch();
@@ -443,9 +441,7 @@ void index_build_graph(ab_index *ix, uint32_t ef_construction) {
                                           static_cast<int>(max_edges), 0, 32, s));
   w.cub_tmp.reserve(w.cub_bytes + 16);
   SearchPlan big = plan_search(AB_QUANT_NONE, ix->raw_chunks, 0, 1.2f, efc, max_batch, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
-  w.bitmap_words = round_up((size_t(n) + 31) / 32, 4);
-  w.slots = big.slots;
-  w.bitmaps.alloc_zero((w.bitmap_words + kSpillList) * w.slots, s);
+  w.visited.prepare(big, n, s);  // sized once for the largest batch; later prepare() calls find everything in place
 
   // ---- upper layers, top down, in a compact id space (position in `order`) ------------------------
   const uint32_t m1 = maxlevel >= 1 ? cnt[1] : 0;

@@ -3,6 +3,7 @@
 // Mirrors the control flow of PyIndex (/root/reference/python/include/index.hpp:85-506).
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <memory>
 
 #include "index.cuh"
@@ -26,6 +27,9 @@ static int guarded(F &&f) {
     return AB_ERR_INVALID;
   }
 }
+
+// for the other translation units of the C ABI (group.cu)
+int guarded_call(const std::function<void()> &f) { return guarded(f); }
 
 static void use_device(const ab_index *ix) { AB_CUDA(cudaSetDevice(ix->device)); }
 
@@ -77,31 +81,53 @@ void index_alloc_spaces(ab_index *ix) {
   ix->removed_node_nbrs.clear();
 }
 
-static void fit_spaces(ab_index *ix, const float *data, uint64_t n, uint32_t dim) {
+// gmin / gmax: quantiser range to use instead of this shard's own (one logical index split over several GPUs must
+// quantise every shard with the global per-dimension range); null = fit on these rows
+void fit_spaces(ab_index *ix, const float *data, uint64_t n, uint32_t dim, const float *gmin, const float *gmax) {
   AB_CHECK(data != nullptr && n > 0 && dim > 0, AB_ERR_INVALID, "fit: empty input");
   AB_CHECK(n < (1ull << 31), AB_ERR_INVALID, "fit: ids are 31-bit (query_utils.hpp:302-306)");
   // RawSpace::fit silently drops rows past capacity and leaves a broken graph (sequential_storage.hpp:77-80);
   // SQ spaces throw (sq8_space.hpp:117-119). Both are reported here.
   AB_CHECK(n <= ix->capacity, AB_ERR_CAPACITY, "The number of data points exceeds the capacity of the space");
   use_device(ix);
+  index_order_after_searches(ix, ix->stream);
+  AB_CUDA(cudaStreamSynchronize(ix->stream));  // buffers may be reallocated below
   index_configure_layout(ix, dim);
   index_alloc_spaces(ix);
   ix->n = ix->n_raw = n;
-  DevBuf<float> staging;
-  const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / (size_t(dim) * 4)));
-  staging.reserve(chunk_rows * dim);
+  // rows may already live on this device (cudaMalloc'd by the caller, e.g. generated there): staged in place
+  cudaPointerAttributes at{};
+  const bool on_device = cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
   const bool cosine = ix->params.metric == AB_METRIC_COS;
-  for (uint64_t r = 0; r < n; r += chunk_rows) {
-    const uint64_t m = std::min(chunk_rows, n - r);
-    AB_CUDA(cudaMemcpyAsync(staging.p, data + r * dim, m * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-    stage_rows(staging.p, ix->raw.p + r * ix->raw_stride, m, dim, ix->raw_stride, cosine, ix->stream);
-    AB_CUDA(cudaStreamSynchronize(ix->stream));
+  if (on_device) {
+    AB_CHECK(at.device == ix->device, AB_ERR_INVALID, "fit: device rows must live on the index's device");
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (1ull << 30) / (size_t(dim) * 4));  // bounded grids
+    for (uint64_t r = 0; r < n; r += chunk_rows) {
+      const uint64_t m = std::min(chunk_rows, n - r);
+      stage_rows(data + r * dim, ix->raw.p + r * ix->raw_stride, m, dim, ix->raw_stride, cosine, ix->stream);
+    }
+  } else {
+    DevBuf<float> staging;
+    const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / (size_t(dim) * 4)));
+    staging.reserve(chunk_rows * dim);
+    for (uint64_t r = 0; r < n; r += chunk_rows) {
+      const uint64_t m = std::min(chunk_rows, n - r);
+      AB_CUDA(cudaMemcpyAsync(staging.p, data + r * dim, m * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+      stage_rows(staging.p, ix->raw.p + r * ix->raw_stride, m, dim, ix->raw_stride, cosine, ix->stream);
+      AB_CUDA(cudaStreamSynchronize(ix->stream));
+    }
   }
   const int q = ix->params.quantization_type;
   if (q != AB_QUANT_NONE) {
     // the SQ space is fitted on the rows as stored by the raw space (normalised for COS, because the
     // reference normalised the caller's buffer in place first: index.hpp:197-206)
-    quant_fit(ix->raw.p, n, dim, ix->raw_stride, ix->qmin.p, ix->qmax.p, ix->stream);
+    if (gmin != nullptr && gmax != nullptr) {
+      AB_CUDA(cudaMemcpyAsync(ix->qmin.p, gmin, dim * sizeof(float), cudaMemcpyDefault, ix->stream));
+      AB_CUDA(cudaMemcpyAsync(ix->qmax.p, gmax, dim * sizeof(float), cudaMemcpyDefault, ix->stream));
+    } else {
+      quant_fit(ix->raw.p, n, dim, ix->raw_stride, ix->qmin.p, ix->qmax.p, ix->stream);
+    }
     quant_encode(q, ix->raw.p, n, dim, ix->raw_stride, ix->qmin.p, ix->qmax.p, ix->codes.p, ix->code_stride, ix->stream);
     quant_tables(q, ix->qmin.p, ix->qmax.p, dim, ix->scale.p, ix->vmin.p, ix->table_len, ix->stream);
   }
@@ -114,6 +140,7 @@ static void fit_spaces(ab_index *ix, const float *data, uint64_t n, uint32_t dim
 void index_upload_graph(ab_index *ix, const uint32_t *adj, const uint32_t *levels, const uint32_t *lists_flat,
                         uint64_t lists_len, uint32_t ep) {
   use_device(ix);
+  index_order_after_searches(ix, ix->stream);
   const uint64_t n = ix->n;
   AB_CHECK(ep < n, AB_ERR_INVALID, "set_graph: entry point out of range");
   AB_CUDA(cudaMemcpyAsync(ix->adj.p, adj, n * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
@@ -154,28 +181,39 @@ void index_download_graph(ab_index *ix, uint32_t *adj, uint32_t *levels, uint32_
   AB_CUDA(cudaStreamSynchronize(ix->stream));
 }
 
+void index_order_after_searches(ab_index *ix, cudaStream_t stream) {
+  if (ix->ws_event_recorded) AB_CUDA(cudaStreamWaitEvent(stream, ix->ws_event, 0));
+}
+
+void index_mark_workspace_use(ab_index *ix, cudaStream_t stream) {
+  if (ix->ws_event == nullptr) AB_CUDA(cudaEventCreateWithFlags(&ix->ws_event, cudaEventDisableTiming));
+  AB_CUDA(cudaEventRecord(ix->ws_event, stream));
+  ix->ws_event_recorded = true;
+}
+
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream, const Scatter *scatter) {
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange) {
   AB_CHECK(ix->has_graph, AB_ERR_STATE, "index is not fitted or loaded");
   AB_CHECK(topk >= 1 && ef >= 1, AB_ERR_INVALID, "topk and ef must be positive");
   // the reference reads uninitialised pool slots when topk > ef (SURVEY.md 8b "Errors"); rejected here
   AB_CHECK(topk <= ef, AB_ERR_INVALID, "topk must not exceed ef");
   AB_CHECK(ef <= 4096, AB_ERR_INVALID, "ef larger than 4096 is not supported");
   if (nq == 0) return;
+  // the workspace below is shared by every launch on this handle: order this one behind the previous user
+  index_order_after_searches(ix, stream);
   const int quant = ix->params.quantization_type;
   const int nchunks = quant == AB_QUANT_NONE ? ix->raw_chunks : ix->code_chunks;
+  const bool need_rerank = rerank && quant != AB_QUANT_NONE;
+  const bool exch_in_search = exchange != nullptr && !need_rerank;
+  AB_CHECK(exchange == nullptr || d_out_dist != nullptr, AB_ERR_INVALID, "the shard exchange needs the distance output");
   SearchPlan plan = plan_search(quant, nchunks, ix->table_len, ix->visit_ratio, ef, static_cast<uint32_t>(nq),
-                                static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
-  // private visited bitmaps, one per resident warp, all-zero between launches
-  const size_t words = round_up((std::max<uint64_t>(ix->capacity, ix->n) + 31) / 32, 4);
-  if (ix->bitmap_words != words || ix->bitmap_slots < plan.slots) {
-    ix->w_bitmaps.alloc_zero((words + kSpillList) * plan.slots, stream);
-    ix->bitmap_words = words;
-    ix->bitmap_slots = plan.slots;
-  }
+                                static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit,
+                                exch_in_search ? size_t(exchange->n_shards) * topk * 8 : 0);
+  // global-memory part of the visited set (overflow tables per resident warp + pooled bitmaps)
+  ix->w_visited.prepare(plan, std::max<uint64_t>(ix->n, 1), stream);
   ix->w_counter.reserve(1);
-  ix->w_stats.reserve(4);
+  ix->w_stats.reserve(8);
   // feedback from earlier launches (visited ids per query size the visited table), without blocking the stream
   if (ix->stats_pending && cudaEventQuery(ix->stats_event) == cudaSuccess) {
     ix->stats_pending = false;
@@ -197,9 +235,8 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
     ix->stats_nq = ix->last_nq;
   }
   AB_CUDA(cudaMemsetAsync(ix->w_counter.p, 0, sizeof(uint32_t), stream));
-  AB_CUDA(cudaMemsetAsync(ix->w_stats.p, 0, 4 * sizeof(unsigned long long), stream));
+  AB_CUDA(cudaMemsetAsync(ix->w_stats.p, 0, 8 * sizeof(unsigned long long), stream));
 
-  const bool need_rerank = rerank && quant != AB_QUANT_NONE;
   if (need_rerank) ix->w_cand.reserve(nq * topk);
 
   SearchArgs a{};
@@ -234,10 +271,10 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   a.pool_sizes = d_pool_sizes;
   a.work_counter = ix->w_counter.p;
   a.hash_size = plan.hash_size;
-  a.bitmaps = ix->w_bitmaps.p;
-  a.bitmap_words = words;
+  ix->w_visited.fill(a);
   a.stats = ix->w_stats.p;
-  if (scatter != nullptr && !need_rerank) a.scatter = *scatter;
+  if (exch_in_search) a.exchange = *exchange;
+  a.pad_empty = (exchange != nullptr && need_rerank) ? 1 : 0;
   launch_search(quant, plan, a, stream);
   ix->last_ef = ef;
   ix->last_nq = nq;
@@ -258,9 +295,10 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
     r.cand_ids = ix->w_cand.p;
     r.out_ids = d_out_ids;
     r.out_dist = d_out_dist;
-    if (scatter != nullptr) r.scatter = *scatter;
+    if (exchange != nullptr) r.exchange = *exchange;
     launch_rerank(r, ix->sm_count, stream);
   }
+  index_mark_workspace_use(ix, stream);
 }
 
 // host queries in, host ids out (PyIndex::batch_search shape)
@@ -315,11 +353,13 @@ static void search_host(ab_index *ix, const float *queries, uint64_t nq, uint32_
     AB_CUDA(cudaMemcpyAsync(pool_dist, ix->w_pool_dist.p, nq * ef * sizeof(float), cudaMemcpyDeviceToHost, s));
     AB_CUDA(cudaMemcpyAsync(pool_sizes, ix->w_pool_sizes.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   }
-  unsigned long long st[4];
+  unsigned long long st[6];
   AB_CUDA(cudaMemcpyAsync(st, ix->w_stats.p, sizeof(st), cudaMemcpyDeviceToHost, s));
   AB_CUDA(cudaStreamSynchronize(s));
   for (int i = 0; i < 4; i++) ix->last_stats[i] = st[i];
   ix->last_stats[4] = nq;
+  ix->last_stats[5] = st[4];
+  ix->last_stats[6] = st[5];
   if (nq >= 32 && ix->last_ef > 0)
     ix->visit_ratio = static_cast<float>(double(st[0]) / double(nq) / double(ix->last_ef)) / visited_model(ix->last_ef);
 }
@@ -388,6 +428,10 @@ void ab_index_destroy(ab_index *index) {
     cudaEventSynchronize(index->stats_event);
     cudaEventDestroy(index->stats_event);
   }
+  if (index->ws_event) {
+    cudaEventSynchronize(index->ws_event);
+    cudaEventDestroy(index->ws_event);
+  }
   if (index->h_stats) cudaFreeHost(index->h_stats);
   delete index;
 }
@@ -396,7 +440,7 @@ int ab_index_fit_spaces(ab_index *index, const float *data, uint64_t n, uint32_t
   return guarded([&] {
     AB_CHECK(index != nullptr, AB_ERR_INVALID, "null index");
     std::lock_guard<std::mutex> lock(index->mu);
-    fit_spaces(index, data, n, dim);
+    fit_spaces(index, data, n, dim, nullptr, nullptr);
   });
 }
 
@@ -405,6 +449,7 @@ int ab_index_build_graph(ab_index *index, uint32_t ef_construction) {
     AB_CHECK(index != nullptr && index->n > 0, AB_ERR_STATE, "fit the spaces first");
     std::lock_guard<std::mutex> lock(index->mu);
     use_device(index);
+    index_order_after_searches(index, index->stream);
     index_build_graph(index, ef_construction);
   });
 }
@@ -415,7 +460,18 @@ int ab_index_fit(ab_index *index, const float *data, uint64_t n, uint32_t dim, u
   return guarded([&] {
     AB_CHECK(index != nullptr, AB_ERR_INVALID, "null index");
     std::lock_guard<std::mutex> lock(index->mu);
-    fit_spaces(index, data, n, dim);
+    fit_spaces(index, data, n, dim, nullptr, nullptr);
+    index_build_graph(index, ef_construction);
+  });
+}
+
+int ab_index_fit_ranged(ab_index *index, const float *data, uint64_t n, uint32_t dim, uint32_t ef_construction, const float *mn,
+                        const float *mx) {
+  return guarded([&] {
+    AB_CHECK(index != nullptr, AB_ERR_INVALID, "null index");
+    AB_CHECK((mn == nullptr) == (mx == nullptr), AB_ERR_INVALID, "min and max go together");
+    std::lock_guard<std::mutex> lock(index->mu);
+    fit_spaces(index, data, n, dim, mn, mx);
     index_build_graph(index, ef_construction);
   });
 }
@@ -525,30 +581,6 @@ int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64
   });
 }
 
-int ab_index_batch_search_scatter_device(ab_index *index, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef,
-                                         int32_t rerank, uint32_t *d_out_ids, float *d_out_dist, uint32_t id_offset,
-                                         uint32_t slot, uint32_t n_dest, const uint64_t *dest_ids, const uint64_t *dest_dist,
-                                         void *stream) {
-  return guarded([&] {
-    AB_CHECK(index != nullptr && d_queries && d_out_ids, AB_ERR_INVALID, "null argument");
-    AB_CHECK(n_dest >= 1 && n_dest <= static_cast<uint32_t>(kMaxDest) && dest_ids && dest_dist, AB_ERR_INVALID,
-             "scatter needs 1..16 destination buffers");
-    Scatter sc{};
-    sc.n_dest = static_cast<int>(n_dest);
-    sc.slot = slot;
-    sc.id_offset = id_offset;
-    for (uint32_t p = 0; p < n_dest; p++) {
-      AB_CHECK(dest_ids[p] != 0 && dest_dist[p] != 0, AB_ERR_INVALID, "null destination buffer");
-      sc.ids[p] = reinterpret_cast<uint32_t *>(static_cast<uintptr_t>(dest_ids[p]));
-      sc.dist[p] = reinterpret_cast<float *>(static_cast<uintptr_t>(dest_dist[p]));
-    }
-    std::lock_guard<std::mutex> lock(index->mu);
-    use_device(index);
-    index_search_device(index, d_queries, nq, topk, ef, rerank != 0, d_out_ids, d_out_dist, nullptr, nullptr, nullptr,
-                        static_cast<cudaStream_t>(stream), &sc);
-  });
-}
-
 int ab_debug_search_plan(int32_t quant, uint32_t row_chunks, uint32_t ef, uint64_t nq, uint64_t n_rows, int32_t sm_count,
                          uint64_t smem_limit, uint64_t out[6]) {
   return guarded([&] {
@@ -566,17 +598,33 @@ int ab_debug_search_plan(int32_t quant, uint32_t row_chunks, uint32_t ef, uint64
   });
 }
 
+static void read_stats(ab_index *index) {
+  std::lock_guard<std::mutex> lock(index->mu);
+  use_device(index);
+  if (index->w_stats.p) {
+    unsigned long long st[6];
+    if (index->ws_event_recorded) AB_CUDA(cudaEventSynchronize(index->ws_event));
+    AB_CUDA(cudaMemcpy(st, index->w_stats.p, sizeof(st), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) index->last_stats[i] = st[i];
+    index->last_stats[5] = st[4];
+    index->last_stats[6] = st[5];
+  }
+}
+
 int ab_index_search_stats(ab_index *index, uint64_t stats[5]) {
   return guarded([&] {
     AB_CHECK(index != nullptr, AB_ERR_INVALID, "null index");
-    std::lock_guard<std::mutex> lock(index->mu);
-    use_device(index);
-    if (index->w_stats.p) {
-      unsigned long long st[4];
-      AB_CUDA(cudaMemcpy(st, index->w_stats.p, sizeof(st), cudaMemcpyDeviceToHost));
-      for (int i = 0; i < 4; i++) index->last_stats[i] = st[i];
-    }
+    read_stats(index);
     for (int i = 0; i < 5; i++) stats[i] = index->last_stats[i];
+  });
+}
+
+int ab_index_search_stats_ex(ab_index *index, uint64_t *stats, uint32_t count) {
+  return guarded([&] {
+    AB_CHECK(index != nullptr && stats != nullptr, AB_ERR_INVALID, "null argument");
+    read_stats(index);
+    for (uint32_t i = 0; i < count; i++) stats[i] = i < 7 ? index->last_stats[i] : 0;
+    if (count > 7) stats[7] = index->w_visited.bytes();
   });
 }
 
@@ -598,6 +646,7 @@ int ab_index_save(ab_index *index, const char *index_path, const char *data_path
     AB_CHECK(index != nullptr && index_path, AB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(index->mu);
     use_device(index);
+    index_order_after_searches(index, index->stream);
     index_save(index, index_path, data_path, quant_path);
   });
 }
@@ -606,6 +655,8 @@ int ab_index_load(ab_index *index, const char *index_path, const char *data_path
     AB_CHECK(index != nullptr && index_path, AB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lock(index->mu);
     use_device(index);
+    index_order_after_searches(index, index->stream);
+    AB_CUDA(cudaStreamSynchronize(index->stream));
     index_load(index, index_path, data_path, quant_path);
   });
 }
@@ -672,6 +723,48 @@ int ab_quant_fit_encode(int32_t quant, const float *data, uint64_t n, uint32_t d
     if (mx) AB_CUDA(cudaMemcpyAsync(mx, dmx.p, dim * 4, cudaMemcpyDeviceToHost, s));
     if (codes) AB_CUDA(cudaMemcpyAsync(codes, dc.p, n * lay.row_bytes, cudaMemcpyDeviceToHost, s));
     AB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int ab_quant_minmax(int32_t metric, const float *data, uint64_t n, uint32_t dim, float *mn, float *mx) {
+  return guarded([&] {
+    require_device();
+    AB_CHECK(data && mn && mx && n > 0 && dim > 0, AB_ERR_INVALID, "empty input");
+    cudaStream_t s = nullptr;
+    cudaPointerAttributes at{};
+    const bool on_device = cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / (size_t(dim) * 4)));
+    DevBuf<float> a, b, dmn, dmx;
+    if (!on_device) a.reserve(chunk * dim);
+    b.reserve(chunk * dim);
+    dmn.reserve(dim);
+    dmx.reserve(dim);
+    std::vector<float> cmn(dim), cmx(dim);
+    std::fill(mn, mn + dim, FLT_MAX);
+    std::fill(mx, mx + dim, -FLT_MAX);
+    for (uint64_t r = 0; r < n; r += chunk) {
+      const uint64_t m = std::min(chunk, n - r);
+      const float *src = data + r * dim;
+      if (!on_device) {
+        AB_CUDA(cudaMemcpyAsync(a.p, src, m * dim * 4, cudaMemcpyHostToDevice, s));
+        src = a.p;
+      }
+      // the SQ space is fitted on the rows as the raw space stores them: normalised for COS (index.hpp:197-206)
+      const float *rows = src;
+      if (metric == AB_METRIC_COS) {
+        stage_rows(src, b.p, m, dim, dim, true, s);
+        rows = b.p;
+      }
+      quant_fit(rows, m, dim, dim, dmn.p, dmx.p, s);
+      AB_CUDA(cudaMemcpyAsync(cmn.data(), dmn.p, dim * 4, cudaMemcpyDeviceToHost, s));
+      AB_CUDA(cudaMemcpyAsync(cmx.data(), dmx.p, dim * 4, cudaMemcpyDeviceToHost, s));
+      AB_CUDA(cudaStreamSynchronize(s));
+      for (uint32_t d = 0; d < dim; d++) {
+        mn[d] = std::min(mn[d], cmn[d]);
+        mx[d] = std::max(mx[d], cmx[d]);
+      }
+    }
   });
 }
 

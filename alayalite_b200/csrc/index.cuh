@@ -57,11 +57,10 @@ struct ab_index {
   ab::DevBuf<uint32_t> w_pool_ids, w_pool_sizes;
   ab::DevBuf<float> w_pool_dist;
   ab::DevBuf<uint32_t> w_counter;            // [1]
-  ab::DevBuf<unsigned long long> w_stats;    // [4]
-  ab::DevBuf<uint32_t> w_bitmaps;
-  size_t bitmap_words = 0;
-  int bitmap_slots = 0;
-  uint64_t last_stats[5] = {0, 0, 0, 0, 0};
+  ab::DevBuf<unsigned long long> w_stats;    // [8] device counters of the last launch (SearchArgs::stats)
+  ab::VisitedWorkspace w_visited;            // overflow tables + pooled bitmaps of the visited set
+  // {ndc, hops, overlay ndc, overflow-table queries, queries, bitmap queries, ids put into overflow tables}
+  uint64_t last_stats[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t last_ef = 0;      // ef of the launch the device counters belong to
   uint64_t last_nq = 0;      // and its query count
   // lag-free feedback for device-resident callers (no synchronisation on their stream): the counters of launch k
@@ -72,6 +71,12 @@ struct ab_index {
   uint32_t stats_ef = 0;
   uint64_t stats_nq = 0;
   float visit_ratio = 0.f;   // visited ids per query / ef over visited_model(ef), from the last counters read back
+  // Ordering contract of the shared workspace (work counter, overflow tables, counters, w_cand): every launch that
+  // uses it records ws_event behind itself, and the next user -- on whatever stream -- waits for that event first.
+  // Searches on one handle therefore never overlap on the device, and insert / remove / build / load order
+  // themselves behind every search already enqueued.
+  cudaEvent_t ws_event = nullptr;
+  bool ws_event_recorded = false;
 };
 
 namespace ab {
@@ -85,12 +90,16 @@ uint64_t index_lists_len(const ab_index *ix);
 // d_queries / outputs are device pointers. cand/pool outputs optional.
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream, const Scatter *scatter = nullptr);
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange = nullptr);
 void index_save(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_load(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_build_graph(ab_index *ix, uint32_t ef_construction);
 uint32_t index_insert(ab_index *ix, const float *vec, uint32_t ef);
 void index_remove(ab_index *ix, uint32_t id);
 void index_sync_valid_bitmap(ab_index *ix);
+// make `stream` wait for every search already enqueued on this handle (any stream); see ab_index::ws_event
+void index_order_after_searches(ab_index *ix, cudaStream_t stream);
+// record the end of a workspace user on `stream`
+void index_mark_workspace_use(ab_index *ix, cudaStream_t stream);
 
 }  // namespace ab

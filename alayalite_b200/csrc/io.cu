@@ -195,6 +195,8 @@ void index_load(ab_index *ix, const char *index_path, const char *data_path, con
   const int quant = ix->params.quantization_type;
   AB_CHECK(quant == AB_QUANT_NONE || (quant_path != nullptr && quant_path[0] != 0), AB_ERR_INVALID,
            "load needs the quantised data file");
+  // a load that fails part-way must not leave a searchable half-overwritten index behind
+  ix->has_graph = false;
 
   // ---- raw space header first: it fixes dim and capacity ----------------------------------------
   File fd(data_path, "rb");
@@ -283,10 +285,12 @@ void index_load(ab_index *ix, const char *index_path, const char *data_path, con
     ix->ov_lists.reserve(std::max<uint64_t>(rows, 1) * 32);
     if (rows) AB_CUDA(cudaMemcpy(ix->ov_lists.p, lists.data(), rows * 32 * 4, cudaMemcpyHostToDevice));
     AB_CUDA(cudaMemcpy(ix->ov_off.p, off.data(), size_t(capacity) * 4, cudaMemcpyHostToDevice));
+    AB_CHECK(ep < ix->n, AB_ERR_IO, "overlay entry point out of range in " + fg.path);
     ix->ep = ep;
     ix->ep_level = ix->h_levels[ep];
   } else {
     AB_CHECK(nep > 0, AB_ERR_IO, "graph has neither overlay nor entry points");
+    AB_CHECK(eps[0] < ix->n, AB_ERR_IO, "graph entry point out of range in " + fg.path);
     ix->ep = eps[0];
     ix->ep_level = 0;
     ix->ov_rows = 0;

@@ -19,6 +19,13 @@ namespace {
 
 // PyIndex::rerank (python/include/index.hpp:450-467): exact raw-space distance for the ef entries of
 // res_pool -- the topk ids search wrote plus (ef - topk) untouched zeros -- ordered by (dist, id).
+__host__ __device__ inline size_t rerank_warp_bytes(const RerankArgs &a) {
+  const uint32_t nz = a.exchange.n_shards > 0 ? 0u : (a.ef - a.topk < a.topk ? a.ef - a.topk : a.topk);
+  const size_t own = size_t(a.nchunks) * 16 + round_up16(size_t(a.topk + nz) * 4) * 2;
+  const size_t scratch = round_up16(size_t(a.exchange.n_shards) * a.topk * 8);
+  return own > scratch ? own : scratch;
+}
+
 template <bool IP, int TPV, int MAXC>
 __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -26,9 +33,10 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
   const int warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
   const size_t q_bytes = size_t(a.nchunks) * 16;
-  const uint32_t nz = min(a.ef - a.topk, a.topk);  // copies of id 0 that can reach the output
+  // copies of id 0 that can reach the output (none when the lists feed a shard exchange: padding is not a row)
+  const uint32_t nz = a.exchange.n_shards > 0 ? 0u : min(a.ef - a.topk, a.topk);
   const uint32_t L = a.topk + nz;
-  const size_t per_warp = q_bytes + round_up16(size_t(L) * 4) * 2;
+  const size_t per_warp = rerank_warp_bytes(a);
   uint8_t *wbase = smem + size_t(warp) * per_warp;
   float *q_raw = reinterpret_cast<float *>(wbase);
   float *ld = reinterpret_cast<float *>(wbase + q_bytes);
@@ -65,7 +73,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
       const uint32_t k = base + g;
       const bool act = k < ndist;
       const uint32_t cv = act ? li[k] : 0u;
-      float d = row_distance<AB_QUANT_NONE, IP, TPV, MAXC>(reinterpret_cast<const uint8_t *>(a.raw) + size_t(cv) * a.raw_stride,
+      const uint32_t cr = cv < a.n_rows ? cv : 0u;  // ids the raw space does not hold score FLT_MAX below; never dereferenced
+      float d = row_distance<AB_QUANT_NONE, IP, TPV, MAXC>(reinterpret_cast<const uint8_t *>(a.raw) + size_t(cr) * a.raw_stride,
                                                           a.nchunks, lg, qs, act);
       if (act && lg == 0) {
         // RawSpace::QueryComputer checks the raw storage's validity bit (raw_space.hpp:297-300): rows the
@@ -90,10 +99,19 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
       if (rank < a.topk) {
         a.out_ids[size_t(qi) * a.topk + rank] = ii;
         if (a.out_dist) a.out_dist[size_t(qi) * a.topk + rank] = di;
-        scatter_store(a.scatter, a.nq, a.topk, qi, rank, ii, di);
       }
     }
     __syncwarp();
+    if (a.exchange.n_shards > 0) {
+      // candidates the traversal padded with 0xFFFFFFFF (pool smaller than topk) sort last: the real ones are a prefix
+      uint32_t nvalid = 0;
+      for (uint32_t i = lane; i < a.topk; i += 32) nvalid += li[i] != kEmptyId ? 1u : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(kFull, nvalid, o);
+      __syncwarp();
+      exchange_epilogue(a.exchange, qi, a.topk, nvalid, a.out_ids + size_t(qi) * a.topk, a.out_dist + size_t(qi) * a.topk,
+                        reinterpret_cast<uint2 *>(wbase), lane);
+    }
   }
 }
 
@@ -138,10 +156,40 @@ void launch_search_raw(const SearchPlan &p, const SearchArgs &a, cudaStream_t s)
 
 }  // namespace
 
+void VisitedWorkspace::prepare(const SearchPlan &plan, uint64_t n_rows, cudaStream_t s) {
+  static const uint32_t big_slots = getenv("AB_BIG_SLOTS") ? static_cast<uint32_t>(std::max(1, atoi(getenv("AB_BIG_SLOTS")))) : 8u;
+  if (plan.ovf_size > ovf_size || plan.slots > slots) {
+    // sized for the most warps any plan can keep resident (24 per SM), so that a plan change between launches --
+    // the visited-ids feedback, another ef -- does not reallocate inside a caller's timed loop
+    ovf_size = std::max(ovf_size, plan.ovf_size);
+    slots = std::max(std::max(slots, plan.slots), plan.max_slots);
+    const size_t words = (size_t(ovf_size) + kSpillList) * size_t(slots);
+    ovf.reserve(words);
+    AB_CUDA(cudaMemsetAsync(ovf.p, 0xFF, words * sizeof(uint32_t), s));
+  }
+  const size_t words = round_up((n_rows + 31) / 32, 4);
+  if (words > big_words || n_big != big_slots) {
+    big_words = std::max(big_words, words);
+    n_big = big_slots;
+    big.alloc_zero(big_words * n_big, s);
+    big_flags.alloc_zero(n_big, s);
+  }
+}
+
+void VisitedWorkspace::fill(SearchArgs &a) const {
+  a.ovf = ovf.p;
+  a.ovf_size = ovf_size;
+  a.ovf_limit = ovf_size - ovf_size / 4;
+  a.big = big.p;
+  a.big_flags = big_flags.p;
+  a.n_big = n_big;
+  a.big_words = big_words;
+}
+
 float visited_model(uint32_t ef) { return 16.0f + 400.0f / static_cast<float>(std::max(1u, ef)); }
 
 SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
-                       int sm_count, size_t smem_limit) {
+                       int sm_count, size_t smem_limit, size_t min_warp_bytes) {
   SearchPlan p{};
   p.tpv = pick_tpv(nchunks);
   static const float hash_factor = getenv("AB_HASH_FACTOR") ? static_cast<float>(atof(getenv("AB_HASH_FACTOR"))) : 1.7f;
@@ -206,6 +254,11 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
     if (h12 < h) h = std::max(512u, h12);
   }
   entry_bytes = quotient(h, p) ? 2 : 4;
+  // the shard exchange merges in the warp's own shared memory: make sure the region is large enough
+  if (other + size_t(h) * entry_bytes < min_warp_bytes) {
+    h = static_cast<uint32_t>((min_warp_bytes - other + entry_bytes - 1) / entry_bytes + 63) & ~63u;
+    entry_bytes = quotient(h, p) ? 2 : 4;
+  }
   p.hash_size = h;
   p.hash_words = h * entry_bytes / 4;
   const size_t pw = other + size_t(p.hash_words) * 4;
@@ -236,6 +289,16 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   const int want_ctas = static_cast<int>((nq + best_wpc - 1) / best_wpc);
   p.ctas = std::max(1, std::min(want_ctas, sm_count * best_ctas));
   p.slots = p.ctas * p.warps_per_cta;
+  p.max_slots = nq >= static_cast<uint32_t>(sm_count) * 24u ? sm_count * 24 : p.slots;
+  // overflow table: room for three times the ids a query is expected to visit, so that the pooled bitmaps stay a
+  // rarely used safety net even when the shared-memory table takes next to nothing
+  static const uint32_t ovf_forced = getenv("AB_OVF_SIZE") ? static_cast<uint32_t>(atoi(getenv("AB_OVF_SIZE"))) : 0u;
+  // (from the model alone, not from this index's measured ratio: the feedback must not reallocate the workspace
+  // in the middle of a caller's loop)
+  uint32_t want = ovf_forced ? ovf_forced : static_cast<uint32_t>(std::min(5.0f * visited_model(ef) * static_cast<float>(ef), 4.0e6f));
+  uint32_t o = ovf_forced ? 64u : 4096u;
+  while (o < want) o <<= 1;
+  p.ovf_size = o;
   return p;
 }
 
@@ -243,7 +306,8 @@ void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args_in,
   SearchArgs args = args_in;
   args.hash_size = plan.hash_size;
   args.hash_words = plan.hash_words;
-  args.hash_limit = plan.hash_size - plan.hash_size / 4;
+  static const int load_pct = getenv("AB_HASH_LOAD") ? std::min(95, std::max(10, atoi(getenv("AB_HASH_LOAD")))) : 75;
+  args.hash_limit = static_cast<uint32_t>(uint64_t(plan.hash_size) * load_pct / 100);  // freeze the table at this load
   args.hash_rbits = plan.hash_rbits;
   args.hash_xshift = plan.hash_xshift;
   args.hash_rmul = plan.hash_rmul;
@@ -260,10 +324,8 @@ void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args_in,
 
 void launch_rerank(const RerankArgs &a, int sm_count, cudaStream_t stream) {
   const int tpv = pick_tpv(a.nchunks);
-  const uint32_t nz = std::min(a.ef - a.topk, a.topk);
-  const uint32_t L = a.topk + nz;
   const int warps = 4;
-  const size_t per_warp = size_t(a.nchunks) * 16 + round_up16(size_t(L) * 4) * 2;
+  const size_t per_warp = rerank_warp_bytes(a);
   const size_t smem = per_warp * warps;
   const int ctas = std::max(1, std::min<int>((a.nq + warps - 1) / warps, sm_count * 8));
   const bool ip = a.metric != AB_METRIC_L2;

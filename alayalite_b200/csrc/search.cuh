@@ -1,23 +1,14 @@
 // Host-visible description of one batched graph search launch (search.cu).
 #pragma once
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace ab {
 
 // Everything the traversal kernel reads, by value. Device pointers unless noted.
-// Multi-GPU exchange fused into the kernel that produces the final lists: besides out_ids / out_dist the
-// results (ids + id_offset) are stored straight into the [slots, nq, topk] gather buffers of every rank of
-// the box -- peer memory mapped over NVLink -- at slot `slot`, so the transfer overlaps the search.
-constexpr int kMaxDest = 16;
-constexpr uint32_t kSpillList = 4096;  // ids remembered per query for the targeted bitmap clean-up
-struct Scatter {
-  int n_dest;  // 0 = off
-  uint32_t slot;
-  uint32_t id_offset;
-  uint32_t *ids[kMaxDest];
-  float *dist[kMaxDest];
-};
-
+// Multi-GPU: see exchange.cuh (the kernel that produces the final lists also delivers them to the owner shard of
+// each query and the last shard to arrive merges).
+constexpr uint32_t kSpillList = 4096;  // overflow-table entries remembered per query for the targeted clean-up
 struct SearchArgs {
   // search space rows: raw floats or SQ codes, row stride in bytes (multiple of 64)
   const uint8_t *rows;
@@ -49,7 +40,9 @@ struct SearchArgs {
   uint32_t *pool_ids;  // [nq, ef] or null
   float *pool_dist;    // [nq, ef] or null
   uint32_t *pool_sizes;
-  Scatter scatter;
+  Exchange exchange;   // raw spaces: the traversal kernel delivers the lists (SQ spaces: the re-rank kernel does)
+  int pad_empty;       // out_ids slots past the pool size get 0xFFFFFFFF instead of the reference's 0 (input of a
+                       // re-rank that feeds an exchange: padding must not masquerade as row 0)
   // scheduling + visited set
   uint32_t *work_counter;       // zeroed before launch
   // visited-set table, filled in by launch_search from the plan
@@ -60,12 +53,20 @@ struct SearchArgs {
   int hash_xshift;              // 32 - bits of the id space
   uint32_t hash_rmul;           // remainder = umulhi(low word of scramble * entries, hash_rmul)
   uint32_t hash_dlimit;         // first invalid entry code (displacement range exhausted)
-  // per-warp visited bitmaps: [slots, bitmap_words + kSpillList] words. The first bitmap_words of a slot are the
-  // bitmap (all zero between launches); the tail is a scratch list of the ids a query put there, so that giving
-  // the bitmap back clean costs a few hundred word stores instead of rewriting N / 8 bytes
-  uint32_t *bitmaps;
-  size_t bitmap_words;
-  unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, spilled queries}
+  // Visited ids that do not fit the shared-memory table continue in the warp's private overflow table in global
+  // memory: [slots, ovf_size + kSpillList] words per slot -- an open-addressing table of ids (all 0xFFFFFFFF between
+  // queries) followed by a scratch list of the entries a query claimed, so that giving the table back clean costs
+  // a few hundred word stores. Its size follows ef, not the number of rows. A query that fills even that (3/4
+  // load) claims one of n_big pooled N-bit bitmaps (the reference's own structure) for the rest of its run.
+  uint32_t *ovf;
+  uint32_t ovf_size;            // entries per slot, power of two
+  uint32_t ovf_limit;           // ids in the overflow table past which the query moves on to a pooled bitmap
+  uint32_t *big;                // [n_big, big_words] bitmaps, all zero while free
+  uint32_t *big_flags;          // [n_big] 0 = free, 1 = claimed
+  uint32_t n_big;
+  size_t big_words;
+  unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, queries that used the overflow table,
+                                //  queries that went on to a pooled bitmap, ids put into overflow tables}
 };
 
 struct RerankArgs {
@@ -80,7 +81,7 @@ struct RerankArgs {
   const uint32_t *cand_ids;  // [nq, topk] search-space top-k
   uint32_t *out_ids;         // [nq, topk]
   float *out_dist;           // [nq, topk] or null
-  Scatter scatter;
+  Exchange exchange;         // n_shards > 0: no zero-fill quirk (only the topk real candidates are re-ranked), lists delivered
 };
 
 // Launch configuration chosen on the host (search.cu)
@@ -94,15 +95,33 @@ struct SearchPlan {
   int hash_rbits, hash_xshift;
   uint32_t hash_rmul, hash_dlimit;
   size_t smem_bytes;
-  int slots;          // ctas * warps_per_cta (bitmap slots needed)
+  int slots;          // ctas * warps_per_cta (overflow-table slots needed)
+  int max_slots;      // slots any plan for this batch size could need (workspace sizing)
+  uint32_t ovf_size;  // entries of one overflow table (power of two)
+};
+
+// Global-memory part of the visited set shared by every launch of one owner (an index, a graph build): one overflow
+// table per resident warp and a small pool of N-bit bitmaps. Memory follows ef and the number of resident warps
+// (about 50 KB per warp at ef 64), not the number of rows; only the pooled bitmaps (8 by default) are N bits each.
+struct VisitedWorkspace {
+  DevBuf<uint32_t> ovf, big, big_flags;
+  uint32_t ovf_size = 0;
+  int slots = 0;
+  uint32_t n_big = 0;
+  size_t big_words = 0;
+  // (re)allocate and initialise when the plan needs more than what is there; stream-ordered on `s`
+  void prepare(const SearchPlan &plan, uint64_t n_rows, cudaStream_t s);
+  void fill(SearchArgs &a) const;
+  size_t bytes() const { return (ovf.n + big.n + big_flags.n) * sizeof(uint32_t); }
 };
 
 // expected visited ids per query divided by ef on SIFT-like graphs
 float visited_model(uint32_t ef);
 // visit_ratio: visited ids per query / ef measured on earlier searches of this index, as a multiple of
 // visited_model(ef) at the ef it was measured with (0 = unknown)
+// min_warp_bytes: shared memory every warp must own at least (scratch of the shard exchange)
 SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
-                       int sm_count, size_t smem_limit);
+                       int sm_count, size_t smem_limit, size_t min_warp_bytes = 0);
 void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);
 // per-quantisation translation units (search_sq8.cu / search_sq4.cu); args already completed by launch_search
 void launch_search_sq8(bool ip, const SearchPlan &plan, const SearchArgs &args, cudaStream_t stream);

@@ -6,7 +6,8 @@
 //   1. holds the 128-byte adjacency row of the node being expanded (one coalesced load, lane j <- neighbour j),
 //   2. filters the neighbours through the visited set: an exact open-addressing table in shared memory (16-bit
 //      quotient entries or 32-bit ids, vote-driven probe loop); a query that outgrows it continues in the warp's
-//      private N-bit bitmap in global memory (the reference's structure) -- never a false "visited" or "new",
+//      private overflow table in global memory (sized from ef, not from the number of rows) and, past that, in a
+//      pooled N-bit bitmap (the reference's structure) -- never a false "visited" or "new",
 //   3. evaluates all unvisited neighbours: sub-warps of TPV lanes per candidate row, 128-bit loads, three candidates
 //      per sub-warp in flight, query chunks read from shared memory after the loads are issued, packed f32x2 math,
 //      dequantisation fused for SQ codes (distance.cuh),
@@ -38,24 +39,107 @@ struct WarpSmem {
   float *cdist;       // [32] their distances
 };
 
-// Visited set of one query. Derived values (the warp's bitmap, table parameters) are recomputed from the
-// kernel arguments where needed instead of living in registers across the hot loop.
+// Visited set of one query: the shared-memory table (level 1), then the warp's overflow table in global memory
+// (level 2), then a pooled N-bit bitmap (level 3). Derived values are recomputed from the kernel arguments where
+// needed instead of living in registers across the hot loop.
 struct Visited {
   uint32_t *hash;
-  bool spilled;      // the hash is frozen, new ids go to the bitmap
-  bool bitmap_used;  // the warp's global bitmap holds bits and must be cleared after the query
-  uint32_t listed;   // ids this query set in the bitmap (the first kSpillList of them are in the slot's list)
+  bool spilled;     // the shared-memory table is frozen, new ids go to the overflow table
+  bool ovf_used;    // the warp's overflow table holds ids and must be cleaned after the query
+  uint32_t listed;  // ids this query put into the overflow table (the first kSpillList entries are listed)
+  int big;          // pooled bitmap this query claimed after filling the overflow table, or -1
 };
 
 // multiply-shift range reduction: any table size, no power-of-two rounding of the shared-memory footprint
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, uint32_t size) { return __umulhi(key * 0x9E3779B1u, size); }
 
-__device__ __forceinline__ uint32_t *bitmap_slot(const SearchArgs &a) {
-  return a.bitmaps + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (a.bitmap_words + kSpillList);
+__device__ __forceinline__ uint32_t *ovf_slot(const SearchArgs &a) {
+  return a.ovf + size_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (size_t(a.ovf_size) + kSpillList);
 }
-__device__ __forceinline__ bool bitmap_test_and_set(const SearchArgs &a, uint32_t key) {
-  const uint32_t bit = 1u << (key & 31);
-  return (atomicOr(&bitmap_slot(a)[key >> 5], bit) & bit) == 0;
+
+// Level 3 of the visited set: claim one of the pooled N-bit bitmaps (rare: a query that fills its overflow table).
+// Warps wait for a free one; holders always finish on their own, so this cannot deadlock.
+__device__ __noinline__ int visit_claim_bitmap(const SearchArgs &a) {
+  int got = 0;
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % a.n_big, tries = 0;
+    while (atomicCAS(&a.big_flags[i], 0u, 1u) != 0u) {
+      i = i + 1 == a.n_big ? 0u : i + 1;
+      if (++tries >= a.n_big) {
+        __nanosleep(2000);
+        tries = 0;
+      }
+    }
+    __threadfence();
+    got = static_cast<int>(i);
+  }
+  return __shfl_sync(kFull, got, 0);
+}
+
+// Levels 2 and 3 of the visited set (warp-collective; `want` marks the lanes whose id was not settled by the
+// shared-memory table). Level 2: the warp's private open-addressing table of ids in global memory; the probe loop
+// is vote-driven like the shared-memory one. Level 3, entered when level 2 reaches 3/4 load: a pooled bitmap;
+// level 2 is then frozen and only read. Returns true for ids seen for the first time.
+__device__ __forceinline__ bool visit_overflow(const SearchArgs &a, Visited &vs, uint32_t key, bool want) {
+  uint32_t *tab = ovf_slot(a);
+  const uint32_t mask = a.ovf_size - 1;
+  const int lane = threadIdx.x & 31;
+  if (vs.big < 0 && vs.listed + 32 > a.ovf_limit) vs.big = visit_claim_bitmap(a);
+  bool is_new = false, pending = want, to_big = false;
+  uint32_t slot = (key * 0x85EBCA6Bu) & mask, mine = 0;
+  while (__any_sync(kFull, pending)) {
+    if (pending) {
+      uint32_t old;
+      if (vs.big < 0) {
+        old = atomicCAS(&tab[slot], kEmptyId, key);
+        if (old == kEmptyId) {
+          is_new = true;
+          mine = slot;
+        }
+      } else {
+        old = __ldcg(&tab[slot]);  // written by this warp's atomics earlier: read at L2, not through L1
+        to_big = old == kEmptyId;
+      }
+      pending = !(old == kEmptyId || old == key);
+      slot = (slot + 1) & mask;
+    }
+  }
+  const uint32_t am = __ballot_sync(kFull, is_new);
+  if (is_new) {  // remember the claimed entry for the clean-up
+    const uint32_t pos = vs.listed + __popc(am & ((1u << lane) - 1));
+    if (pos < kSpillList) tab[a.ovf_size + pos] = mine;
+  }
+  vs.listed += __popc(am);
+  vs.ovf_used = true;
+  if (vs.big >= 0) {
+    if (to_big) {
+      const uint32_t bit = 1u << (key & 31);
+      is_new = (atomicOr(&a.big[size_t(vs.big) * a.big_words + (key >> 5)], bit) & bit) == 0;
+    }
+    __syncwarp();
+  }
+  return is_new;
+}
+
+// give the overflow table (and a claimed bitmap) back clean
+__device__ __noinline__ void visit_overflow_release(const SearchArgs &a, Visited &vs) {
+  uint32_t *tab = ovf_slot(a);
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (vs.listed <= kSpillList) {
+    for (uint32_t i = lane; i < vs.listed; i += 32) tab[tab[a.ovf_size + i]] = kEmptyId;
+  } else {
+    uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+    for (uint32_t w = lane; w < a.ovf_size / 4; w += 32) t4[w] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
+  }
+  if (vs.big >= 0) {
+    uint4 *bm = reinterpret_cast<uint4 *>(a.big + size_t(vs.big) * a.big_words);
+    for (size_t w = lane; w < a.big_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(&a.big_flags[vs.big], 0u);
+  }
+  __syncwarp();
 }
 
 // Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
@@ -72,7 +156,7 @@ __device__ __forceinline__ bool bitmap_test_and_set(const SearchArgs &a, uint32_
 //    entry equal to (displacement, r) at slot home + displacement can only belong to this id. Half the
 //    shared memory per warp, which matters twice: more resident warps, and more of the unified L1/shared
 //    array left to stage loads in flight. A probe that runs out of displacement range falls through to
-//    the warp's bitmap (exact, rare).
+//    the warp's overflow table (exact).
 __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t key, bool active) {
   const uint32_t hsize = a.hash_size;
   bool is_new = false;
@@ -133,29 +217,10 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
     }
   }
   if (__any_sync(kFull, to_bitmap)) {
-    bool added = false;
-    if (to_bitmap) added = is_new = bitmap_test_and_set(a, key);
-    const uint32_t am = __ballot_sync(kFull, added);
-    if (added) {  // remember the id for the clean-up
-      const uint32_t pos = vs.listed + __popc(am & ((1u << (threadIdx.x & 31)) - 1));
-      if (pos < kSpillList) bitmap_slot(a)[a.bitmap_words + pos] = key;
-    }
-    vs.listed += __popc(am);
-    vs.bitmap_used = true;
-    __syncwarp();
+    const bool r = visit_overflow(a, vs, key, to_bitmap);
+    if (to_bitmap) is_new = r;
   }
   return is_new;
-}
-
-// one (id, distance) of the final list of query qi -> slot `slot` of every rank's gather buffer (peer stores)
-__device__ __forceinline__ void scatter_store(const Scatter &sc, uint32_t nq, uint32_t topk, uint32_t qi, uint32_t pos,
-                                              uint32_t id, float dist) {
-  if (sc.n_dest == 0) return;
-  const size_t o = (size_t(sc.slot) * nq + qi) * topk + pos;
-  for (int p = 0; p < sc.n_dest; p++) {
-    sc.ids[p][o] = id + sc.id_offset;
-    sc.dist[p][o] = dist;
-  }
 }
 
 // LinearPool::insert (query_utils.hpp:254-272); warp-collective, all arguments warp-uniform.
@@ -254,6 +319,64 @@ __device__ __forceinline__ void pool_merge(uint2 *pool, const float *cdist, uint
   __syncwarp();
   if (valid0 && n0 < ef) pool[n0] = e0;
   if (valid1 && n1 < ef) pool[n1] = e1;
+  if (accept && mypos < ef) pool[mypos] = make_uint2(__float_as_uint(d), lane == sel ? (v | kCheckedBit) : v);
+  __syncwarp();
+  size = nsize;
+  cur = c;
+}
+
+// The same merge for any pool size (used above ef = 64). Every accepting lane finds its candidate's upper bound p
+// in the sorted pool by binary search (all lanes in parallel, log2(size) + 1 uniform steps). With
+//   before_j = accepted candidates ordered before j (smaller distance, or equal distance and earlier slot)
+// candidate j lands at f_j = p_j + before_j; these final positions are distinct, and the old entries fill the
+// remaining positions in their old order. So the new pool is produced by DESTINATION: for position f that no
+// candidate takes, the source is old entry f - #{j : f_j < f}. Per 32-position tile that is one redux.or (which
+// positions of the tile go to candidates), one vote (how many candidates land below the tile) and a popc per lane,
+// independent of the number of accepted candidates. Tiles are rewritten from the top down to the tile of the
+// smallest f_j: a tile reads sources at or below its own positions, and everything above it is already final, so
+// no write can land on an entry that is still to be read; the candidates are stored last. Whatever would end at
+// index >= ef is never copied. One pass replaces up to 32 sequential LinearPool::insert calls.
+__device__ __forceinline__ void pool_merge_tiles(uint2 *pool, int &size, int &cur, int ef, uint32_t acc, int sel, bool accept,
+                                                 float d, uint32_t v, int lane) {
+  // 1. upper bound of every accepted candidate
+  int p = 0;
+  for (int b = 1 << (31 - __clz(size | 1)); b > 0; b >>= 1) {
+    const int t = p + b;
+    if (accept && t <= size && __uint_as_float(pool[t - 1].x) <= d) p = t;
+  }
+  const int nacc = __popc(acc);
+  // 2. rank among the accepted candidates
+  int before = 0;
+  for (uint32_t rest = acc; rest;) {
+    const int j = __ffs(rest) - 1;
+    rest &= rest - 1;
+    const float dj = __shfl_sync(kFull, d, j);
+    before += (accept && lane != j && (dj < d || (dj == d && j < lane))) ? 1 : 0;
+  }
+  const int mypos = accept ? p + before : 0x7FFFFFFF;
+  // cursor: new index of the entry it pointed at, or the first un-expanded insert before it
+  int c;
+  if (cur < size) {
+    c = cur + __popc(__ballot_sync(kFull, accept && p <= cur));
+  } else {
+    c = size + nacc;
+  }
+  const int nsize = min(size + nacc, ef);
+  const int ins = (accept && lane != sel && mypos < ef) ? mypos : 0x7FFFFFFF;
+  c = min(min(c, nsize), static_cast<int>(__reduce_min_sync(kFull, static_cast<unsigned>(ins))));
+  // 3. rewrite positions fmin .. nsize - 1, top tile first
+  const int fmin = static_cast<int>(__reduce_min_sync(kFull, static_cast<unsigned>(mypos)));
+  for (int base = (nsize - 1) & ~31; base >= 0 && base + 31 >= fmin; base -= 32) {
+    const uint32_t taken = __reduce_or_sync(kFull, (mypos >> 5) == (base >> 5) ? (1u << (mypos & 31)) : 0u);
+    const int below = __popc(__ballot_sync(kFull, mypos < base));
+    const int f = base + lane;
+    const bool mv = f < nsize && f >= fmin && ((taken >> lane) & 1u) == 0;
+    uint2 e = make_uint2(0u, 0u);
+    if (mv) e = pool[f - below - __popc(taken & ((1u << lane) - 1))];
+    __syncwarp();
+    if (mv) pool[f] = e;
+  }
+  __syncwarp();
   if (accept && mypos < ef) pool[mypos] = make_uint2(__float_as_uint(d), lane == sel ? (v | kCheckedBit) : v);
   __syncwarp();
   size = nsize;
@@ -499,8 +622,9 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     uint32_t nvis = 0;
     uint32_t ndc = 0, hops = 0, ndc_ov = 0;  // per query: far below 2^32
     vs.spilled = false;
-    vs.bitmap_used = false;
+    vs.ovf_used = false;
     vs.listed = 0;
+    vs.big = -1;
 
     // ---- entry point: OverlayGraph::initialize (overlay_graph.hpp:122-144) ---------------------
     uint32_t u = a.ep;
@@ -628,19 +752,13 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       }
       const uint32_t v_next = a.adj[size_t(u) * kR + lane];
 
-      // inserts in neighbour order: one merge step when the pool fits two entries per lane, else one by one
-      if (ef <= 64) {
-        if (acc) pool_merge(ws.pool, ws.cdist, newmask, size, cur, ef, acc, sel, accept, d, v, lane);
-        acc = 0;
-      }
-      while (acc) {
-        const int j = __ffs(acc) - 1;
-        acc &= acc - 1;
-        const int rj = __popc(newmask & ((1u << j) - 1));
-        const float dj = ws.cdist[rj];
-        const uint32_t vj = ws.cand[rj];
-        if (size == ef && dj >= __uint_as_float(ws.pool[size - 1].x)) continue;
-        pool_insert(ws.pool, size, cur, ef, dj, j == sel ? (vj | kCheckedBit) : vj, lane, j == sel);
+      // inserts in neighbour order, all accepted candidates of the hop in one merge step
+      if (acc) {
+        if (ef <= 64) {
+          pool_merge(ws.pool, ws.cdist, newmask, size, cur, ef, acc, sel, accept, d, v, lane);
+        } else {
+          pool_merge_tiles(ws.pool, size, cur, ef, acc, sel, accept, d, v, lane);
+        }
       }
       // the closest un-expanded entry is the likely hop after this one: pull its adjacency row towards L2
       if (lane == 0 && cur < size) {
@@ -654,11 +772,11 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     // ---- results ----------------------------------------------------------------------------
     for (uint32_t i = lane; i < a.topk; i += 32) {
       const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
-      const uint32_t rid = in ? (ws.pool[i].y & kIdMask) : 0u;
+      uint32_t rid = in ? (ws.pool[i].y & kIdMask) : 0u;
       const float rd = in ? __uint_as_float(ws.pool[i].x) : 0.f;
+      if (a.pad_empty && static_cast<int>(i) >= size) rid = kEmptyId;
       a.out_ids[size_t(qi) * a.topk + i] = rid;
       if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = rd;
-      scatter_store(a.scatter, a.nq, a.topk, qi, i, rid, rd);
     }
     if (a.pool_ids) {
       for (int i = lane; i < ef; i += 32) {
@@ -667,22 +785,22 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
       }
       if (lane == 0) a.pool_sizes[qi] = size;
     }
-    if (vs.bitmap_used) {
-      // give the private bitmap back all-zero (the reference allocates + zeroes one per query): only the words of
-      // the listed ids, or the whole bitmap if the list overflowed
-      uint32_t *bmw = bitmap_slot(a);
+    if (a.exchange.n_shards > 0) {
+      // shard exchange: deliver this list to the query's owner; the last shard to arrive merges (exchange.cuh).
+      // The warp's whole shared-memory region is free by now and serves as merge scratch.
       __syncwarp();
-      if (vs.listed <= kSpillList) {
-        for (uint32_t i = lane; i < vs.listed; i += 32) bmw[bmw[a.bitmap_words + i] >> 5] = 0u;
-      } else {
-        uint4 *bm = reinterpret_cast<uint4 *>(bmw);
-        for (size_t w = lane; w < a.bitmap_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
-      }
+      exchange_epilogue(a.exchange, qi, a.topk, min(static_cast<uint32_t>(size), a.topk), a.out_ids + size_t(qi) * a.topk,
+                        a.out_dist + size_t(qi) * a.topk, reinterpret_cast<uint2 *>(wbase), lane);
     }
+    if (vs.ovf_used) visit_overflow_release(a, vs);
     if (lane == 0) {
       atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
       atomicAdd(&a.stats[1], static_cast<unsigned long long>(hops));
-      if (vs.bitmap_used) atomicAdd(&a.stats[3], 1ull);
+      if (vs.ovf_used) {
+        atomicAdd(&a.stats[3], 1ull);
+        atomicAdd(&a.stats[5], static_cast<unsigned long long>(vs.listed));
+      }
+      if (vs.big >= 0) atomicAdd(&a.stats[4], 1ull);
     }
     __syncwarp();
   }

@@ -191,6 +191,8 @@ void index_remove(ab_index *ix, uint32_t id) {
   AB_CUDA(cudaSetDevice(ix->device));
   AB_CHECK(ix->has_graph, AB_ERR_STATE, "Index is not init yet");
   AB_CHECK(id < ix->capacity, AB_ERR_INVALID, "id out of range");
+  // searches enqueued on other streams read adj / valid: let them finish first
+  if (ix->ws_event_recorded) AB_CUDA(cudaEventSynchronize(ix->ws_event));
   uint32_t row[32];
   AB_CUDA(cudaMemcpy(row, ix->adj.p + size_t(id) * 32, 128, cudaMemcpyDeviceToHost));
   for (int j = 0; j < 32; j++) {

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["low_rank", "uniform", "integer_grid", "CONFIGS"]
+__all__ = ["low_rank", "low_rank_device", "uniform", "integer_grid", "CONFIGS", "BLOCK_ROWS"]
 
 # name -> (n, dim, nq, latent L, metric, quant, topk)
 CONFIGS = {
@@ -59,3 +59,54 @@ def integer_grid(n: int, dim: int, nq: int, seed: int = 7, hi: int = 16):
     are independent of summation order and must match the reference bit for bit, ties included."""
     rng = np.random.default_rng(seed)
     return (rng.integers(0, hi, (n, dim)).astype(np.float32), rng.integers(0, hi, (nq, dim)).astype(np.float32))
+
+
+BLOCK_ROWS = 250_000
+
+
+def low_rank_device(n: int, dim: int, nq: int, latent: int = 16, seed: int = 42, noise: float = 0.05, normalize: bool = False,
+                    device="cuda", first_block: int = 0):
+    """The same latent model generated on the GPU (torch Philox streams; plumbing, not a kernel of the path) for the
+    benchmark's large configurations, where numpy on the host would take longer than the measurement.
+
+    The base set is a sequence of BLOCK_ROWS-row blocks, block b drawn from its own stream seeded (seed, b), so a shard
+    that owns rows [first_block * BLOCK_ROWS, first_block * BLOCK_ROWS + n) of a larger set generates exactly those
+    rows, whatever the number of shards. Queries come from the stream (seed, 'q') and are the same for everybody.
+    Returns (base [n, dim], queries [nq, dim]) as float32 tensors on `device`. Reproducible for a given GPU model and
+    torch build -- which is all the two arms of bench.py, run on the same box, need."""
+    import math
+
+    import torch
+
+    dev = torch.device(device)
+
+    def stream(tag):
+        g = torch.Generator(device=dev)
+        g.manual_seed((seed * 1_000_003 + tag) & 0x7FFFFFFFFFFFFFFF)
+        return g
+
+    a = torch.randn((latent, dim), generator=stream(1 << 40), device=dev) / math.sqrt(latent)
+
+    def draw(m, g, out):
+        z = torch.randn((m, latent), generator=g, device=dev)
+        torch.matmul(z, a, out=out)
+        out.add_(torch.randn((m, dim), generator=g, device=dev), alpha=noise)
+        if normalize:
+            out.div_(out.norm(dim=1, keepdim=True))
+
+    base = torch.empty((n, dim), dtype=torch.float32, device=dev)
+    done, b = 0, first_block
+    while done < n:
+        g = stream(b)
+        m = min(BLOCK_ROWS, n - done)
+        if m == BLOCK_ROWS:
+            draw(m, g, base[done:done + m])
+        else:  # a partial last block is the head of the full block (keeps rows independent of n)
+            tmp = torch.empty((BLOCK_ROWS, dim), dtype=torch.float32, device=dev)
+            draw(BLOCK_ROWS, g, tmp)
+            base[done:done + m] = tmp[:m]
+        done += m
+        b += 1
+    q = torch.empty((nq, dim), dtype=torch.float32, device=dev)
+    draw(nq, stream((1 << 40) + 1), q)
+    return base, q

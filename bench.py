@@ -1,23 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- batch_search QPS at recall@10 >= 0.95 on the SIFT-1M-shaped config (BASELINE.json configs[1]).
+"""bench.py -- batch_search QPS at recall@10 >= 0.95, measured on the north-star target configuration
+(synthetic 10M x 128 fp32, L2; BASELINE.json north_star) with the other BASELINE configs as extra blocks.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--blocks main,c2,bf,c3,c4]
 
-One "step" = one batch_search pass over the 10 000 synthetic queries at the smallest ef whose
-recall@10 against exact ground truth is >= 0.95. Prints ONE JSON line (rank 0).
+One "step" = one batch_search pass over the 10 000 synthetic queries at the smallest ef whose recall@10 against
+exact ground truth is >= 0.95. Prints ONE JSON line (rank 0).
 
-ours      index built on the GPU through the C ABI (ab_index_fit); `value` = QPS with queries and
-          results resident in HBM (ab_index_batch_search_device, CUDA events); `e2e` = the same
-          search through the reference-facing call ab_index_batch_search with pinned HOST buffers
-          (H2D of the queries and D2H of the ids inside the timed region).
-reference the reference's own CPU path (oracle/_ref: unmodified headers compiled in place; the exact
-          PyIndex::batch_search route = coroutine Scheduler on every host thread) on the same data,
-          same metric. Falls back to the oracle port if oracle/_ref is absent.
-N > 1     one process per GPU (torchrun). Every rank owns one 1M-vector shard (ids offset by
-          rank * 1M), searches all queries on it, and the per-shard top-k lists are all-gathered over
-          NCCL and merged on the device. Weak scaling: the indexed set grows with N.
-          `value` counts (query, shard) searches per second -- the unit every rank processes -- and
-          `merged_qps` is the end-user query rate over the N x 1M union.
+ours       The index is built on the GPU through the C ABI (ab_index_fit). `value` = QPS with queries and results
+           resident in HBM (ab_index_batch_search_device, CUDA events on the launching stream, L2 flushed between
+           steps). `e2e` = the same search through the reference-facing API with HOST buffers, host<->device copies
+           inside the timed region: `e2e.value` is alayalite_b200.Index.batch_search(numpy) -- the call a user of the
+           reference SDK makes (pybind -> C ABI, pageable numpy arrays) -- and `e2e.pinned` the C-ABI call on pinned
+           buffers. Extra blocks of the same line: `c2` (1M x 128, BASELINE configs[1]), `c3` (1M x 960 SQ8),
+           `c4` (5M x 768 IP SQ4 top-100), `bruteforce` (tcgen05 exact top-k, 1M x 128 x 10k). Each carries its own
+           roofline, recall and CPU baseline; a block that would overrun the time budget is listed as skipped.
+reference  The reference's own CPU search (oracle/_ref: unmodified headers compiled in place; the exact
+           PyIndex::batch_search route = coroutine Scheduler on every host thread) on the same rows, queries and
+           metric. At 10M rows the reference's own CPU build takes minutes, so its graph is the one ab_index_fit
+           builds on the GPU, handed over through the reference's own file formats (Graph::load, RawSpace::load):
+           both arms search the same graph, and the timed code is the reference's. `--ref-build own` lets the
+           reference build its own index instead.
+N > 1      One process per GPU (torchrun). Layout = shards x replicas (--layout SxR; default 1xN): a replica group
+           holds the whole index split by contiguous id ranges over S GPUs (peer-store exchange fused into the search
+           kernel, merge by the last shard to arrive), and the R groups answer different query batches. `value` is
+           ALWAYS end-user queries per second -- every query counted once, whatever the number of shards.
+           Extra blocks: `sharded` (the same 10M set split over N shards, strong scaling) and, at N = 8, `c5`
+           (100M x 96 over 8 shards).
 """
 
 from __future__ import annotations
@@ -25,8 +34,10 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,13 +47,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "batch_search QPS at recall@10>=0.95"
-WORKLOAD = "sift1m-shape: synthetic low-rank(L=16) 1M x 128 fp32, L2, HNSW R=32 efc=100, 10k queries, top-10"
-N_BASE, DIM, NQ, LATENT, TOPK, EFC = 1_000_000, 128, 10_000, 16, 10, 100
-EF_SWEEP = (10, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 100, 128, 160, 200, 300, 400, 800)
-TARGET_RECALL = 0.95
+EFC = 100
+EF_SWEEP = (10, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 90, 100, 116, 128, 144, 160, 180, 200, 240, 280, 340, 400, 500, 640, 800)
+
+# name -> workload. `latent` is the rank of the generator; SQ configs are calibrated so that the
+# operating point lands at ef 50-200 like the survey asks.
+CONFIGS = {
+    "main": dict(n=10_000_000, dim=128, nq=10_000, latent=16, metric="l2", quant="none", topk=10, target=0.95,
+                 workload="north-star target: synthetic low-rank(L=16) 10M x 128 fp32, L2, HNSW R=32 efc=100, 10k queries, top-10"),
+    "c2": dict(n=1_000_000, dim=128, nq=10_000, latent=16, metric="l2", quant="none", topk=10, target=0.95,
+               workload="configs[1] sift1m-shape: synthetic low-rank(L=16) 1M x 128 fp32, L2, 10k queries, top-10"),
+    "c3": dict(n=1_000_000, dim=960, nq=10_000, latent=24, metric="l2", quant="sq8", topk=10, target=0.95,
+               workload="configs[2] gist960-shape: synthetic low-rank(L=24) 1M x 960 fp32, L2, SQ8 search space + raw re-rank, 10k queries, top-10"),
+    "c4": dict(n=5_000_000, dim=768, nq=10_000, latent=24, metric="ip", quant="sq4", topk=100, target=0.95, normalize=True,
+               workload="configs[3] rag768-shape: synthetic low-rank(L=24) 5M x 768 fp32 L2-normalised, inner product, SQ4 search space + raw re-rank, 10k queries, top-100"),
+    "c5": dict(n=100_000_000, dim=96, nq=10_000, latent=24, metric="l2", quant="none", topk=10, target=0.95,
+               workload="configs[4] deep100m-shape: synthetic low-rank(L=24) 100M x 96 fp32, L2, id-range shards, 10k queries, top-10"),
+}
 
 
 def recall_at_k(res, gt):
+    res = np.asarray(res).astype(np.int64)
+    gt = np.asarray(gt).astype(np.int64)
     hits = 0
     for r, g in zip(res, gt):
         hits += len(set(r.tolist()) & set(g.tolist()))
@@ -53,21 +79,13 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def load_traffic():
-    """dram bytes per launch of the traversal kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f).get("total")
-    return None
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1656.1)), "measured (MEASURED_PEAKS.json: hbm_gbs burst copy, bf16_tflops burst)"
+    return 6650.0, 1650.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.65 PF/s bf16)"
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 25 ms while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -110,268 +128,438 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class Budget:
+    def __init__(self, seconds):
+        self.t0, self.limit = time.time(), seconds
+
+    def left(self):
+        return self.limit - (time.time() - self.t0)
+
+
 # --------------------------------------------------------------------------------------------------
-def reference_arm(args, rank, world):
-    """The reference's CPU implementation of the path, all host threads, same data and metric."""
-    if rank != 0:
-        return
-    from alayalite_b200.synthetic import low_rank
+# the reference's CPU search on a given index (cpu_baseline leg and --impl reference)
+def save_for_reference(ix, folder, quant):
+    os.makedirs(folder, exist_ok=True)
+    paths = (os.path.join(folder, "g.index"), os.path.join(folder, "raw.data"), os.path.join(folder, "sq.data") if quant != "none" else "")
+    ix.save(*paths)
+    return paths
+
+
+def reference_on_files(cfg, paths, q_host, gt, threads, steps, warmup, sample_nq, capacity):
+    """Load an index in the reference's file formats into the UNMODIFIED reference and time its batch_search route.
+    Returns (qps, ef, recall, detail)."""
+    from oracle import oracle as O
+
+    chk = O.Checker("ref")
+    idx = chk.index(cfg["metric"], cfg["quant"], capacity, cfg["dim"])
+    t0 = time.time()
+    idx.load(*paths)
+    load_s = time.time() - t0
+    k = cfg["topk"]
+    ns = min(500, len(q_host))
+    ef, rec = EF_SWEEP[-1], 0.0
+    for e in EF_SWEEP:
+        if e < k:
+            continue
+        rec = recall_at_k(idx.batch_search(q_host[:ns], k, e, threads), gt[:ns])
+        if rec >= cfg["target"]:
+            ef = e
+            break
+        if cfg["quant"] != "none" and e >= 400:
+            ef = e
+            break
+    qs = np.ascontiguousarray(q_host[:sample_nq])
+    for _ in range(warmup):
+        idx.batch_search_inplace(qs, k, ef, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        idx.batch_search_inplace(qs, k, ef, threads)
+    dt = time.perf_counter() - t0
+    qps = len(qs) * steps / dt
+    t0 = time.perf_counter()
+    idx.batch_search_inplace(qs, k, ef, threads, solo=True)
+    solo = len(qs) / (time.perf_counter() - t0)
+    detail = dict(load_s=load_s, solo_qps=solo, simd=chk.simd_level(), ms_per_step=dt / steps * 1e3, nq=len(qs))
+    return qps, ef, rec, detail
+
+
+# --------------------------------------------------------------------------------------------------
+def make_index(cfg, d_base, local_rank, n=None):
+    """SDK Index (the object a user holds) whose native handle is fitted from rows already on the device."""
+    from alayalite_b200 import _cabi
+    from alayalite_b200._alayalitepy import PyIndexInterface
+    from alayalite_b200.index import Index
+    from alayalite_b200.schema import IndexParams
+
+    n = d_base.shape[0] if n is None else n
+    params = IndexParams(index_type="hnsw", data_type=np.float32, id_type=np.uint32, quantization_type=cfg["quant"], metric=cfg["metric"], capacity=n)
+    params.fill_none_values()
+    sdk = Index("bench", params)
+    sdk._native = PyIndexInterface(params.to_cpp_params())
+    sdk._dim = cfg["dim"]
+    ix = _cabi.NativeIndex(cfg["metric"], cfg["quant"], n, handle=sdk._native._handle())
+    t0 = time.time()
+    ix.fit_ptr(d_base.data_ptr(), n, cfg["dim"], EFC)
+    return sdk, ix, time.time() - t0
+
+
+def ground_truth(cfg, d_base, d_q, stream, torch):
+    from alayalite_b200 import _cabi
+
+    nq, k = d_q.shape[0], cfg["topk"]
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device=d_q.device)
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device=d_q.device)
+    _cabi.bruteforce_topk_device(cfg["metric"], d_base.data_ptr(), d_base.shape[0], cfg["dim"], d_q.data_ptr(), nq, k, d_ids.data_ptr(), d_dist.data_ptr(), stream)
+    torch.cuda.synchronize()
+    return d_ids, d_dist
+
+
+def row_bytes_of(cfg):
+    d = cfg["dim"]
+    b = {"none": d * 4, "sq8": d, "sq4": (d + 1) // 2}[cfg["quant"]]
+    return (b + 63) // 64 * 64  # whole 64-byte-strided rows are fetched
+
+
+def algorithmic_bytes(cfg, stats):
+    """(ndc_L0 + ndc_overlay) * row_bytes + hops * R * 4, plus the raw rows of the re-rank for SQ spaces
+    (topk ids + id 0: what the reference's re-rank over a zero-filled res_pool really touches)."""
+    b = (stats["ndc"] + stats["overlay"]) * row_bytes_of(cfg) + stats["hops"] * 128
+    if cfg["quant"] != "none":
+        b += stats["queries"] * (cfg["topk"] + 1) * ((cfg["dim"] * 4 + 63) // 64 * 64)
+    return b
+
+
+def pick_ef(search_ids, cfg, gt, cap=None):
+    """smallest ef of the sweep reaching the target recall (SQ configs: the reference's re-rank only sees the top-k of
+    the code space, so recall saturates below 1; the sweep then stops where recall stops improving)."""
+    k = cfg["topk"]
+    best = (0.0, None)
+    hist = []
+    for e in EF_SWEEP:
+        if e < k or (cap and e > cap):
+            continue
+        rec = recall_at_k(search_ids(e), gt)
+        hist.append((e, round(rec, 4)))
+        if rec >= cfg["target"]:
+            return e, rec, True, hist
+        if rec > best[0] + 0.002:
+            best = (rec, e)
+        elif cfg["quant"] != "none" and e >= 2 * (best[1] or e):
+            break
+    return best[1] or EF_SWEEP[-1], best[0], False, hist
+
+
+def run_block(name, cfg, args, torch, dev, local_rank, stream, peaks, cpu=True, clocks=None):
+    """Build, find the operating point, time device-resident and end-to-end, roofline, CPU baseline."""
+    from alayalite_b200 import _cabi
+    from alayalite_b200.synthetic import low_rank_device
+
+    n, dim, nq, k = cfg["n"], cfg["dim"], cfg["nq"], cfg["topk"]
+    t_block = time.time()
+    d_base, d_q = low_rank_device(n, dim, nq, cfg["latent"], seed=42, normalize=cfg.get("normalize", False), device=dev)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t_block
+    sdk, ix, build_s = make_index(cfg, d_base, local_rank)
+    gt_ids, _ = ground_truth(cfg, d_base, d_q, stream, torch)
+    gt = gt_ids.cpu().numpy()
+    del d_base, gt_ids
+    torch.cuda.empty_cache()
+
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+
+    def search_ids(ef):
+        ix.batch_search_device(d_q.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), True, stream)
+        torch.cuda.synchronize()
+        return d_ids.cpu().numpy()
+
+    ef, rec, met, hist = pick_ef(search_ids, cfg, gt)
+
+    # ---- device-resident: K steps, CUDA events on the launching stream, L2 flushed between steps ----
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        ix.batch_search_device(d_q.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), True, stream)
+    torch.cuda.synchronize()
+    launches0 = _cabi.kernel_launch_count()
+    times = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ctx = clocks if clocks is not None else ClockSampler(local_rank)
+    with ctx:
+        for _ in range(args.steps):
+            flush.zero_()
+            ev[0].record()
+            ix.batch_search_device(d_q.data_ptr(), nq, k, ef, d_ids.data_ptr(), d_dist.data_ptr(), True, stream)
+            ev[1].record()
+            torch.cuda.synchronize()
+            times.append(ev[0].elapsed_time(ev[1]))
+    launches = _cabi.kernel_launch_count() - launches0
+    stats = ix.stats()
+    del flush
+    ms = float(np.mean(times))
+
+    # ---- end to end: host buffers in, host ids out ---------------------------------------------------
+    q_host = d_q.cpu().numpy()
+    res = None
+    for _ in range(2):
+        res = sdk.batch_search(q_host, k, ef)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = sdk.batch_search(q_host, k, ef)
+    e2e_numpy = nq * args.steps / (time.perf_counter() - t0)
+    e2e_recall = recall_at_k(res, gt)
+    qt = torch.from_numpy(q_host).pin_memory()
+    h_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        ix.batch_search_ptr(qt.data_ptr(), nq, k, ef, h_ids.data_ptr())
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ix.batch_search_ptr(qt.data_ptr(), nq, k, ef, h_ids.data_ptr())
+    e2e_pinned = nq * args.steps / (time.perf_counter() - t0)
+
+    hbm, _, peak_src = peaks
+    alg = algorithmic_bytes(cfg, stats)
+    achieved = alg / (ms * 1e-3) / 1e9
+    out = {
+        "workload": cfg["workload"], "ef": ef, "recall": rec, "recall_k": k, "target_met": met, "recall_by_ef": hist[-6:],
+        "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "ms_min": float(min(times)), "steps": args.steps,
+        "e2e": {"value": e2e_numpy, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 4,
+                "api": "alayalite_b200.Index.batch_search(numpy) -> pybind -> ab_index_batch_search (pageable host buffers)",
+                "recall": e2e_recall, "pinned": e2e_pinned, "pinned_api": "ab_index_batch_search on pinned host buffers (read / written in place by the kernels)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "kernel": "beam_search_kernel" + (" + rerank_kernel" if cfg["quant"] != "none" else ""), "kernel_ms": ms,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                     "per_query": {"ndc_level0": stats["ndc"] / nq, "ndc_overlay": stats["overlay"] / nq, "hops": stats["hops"] / nq, "bytes": alg / nq,
+                                   "row_bytes": row_bytes_of(cfg), "overflow_table_ids": stats["overflow_ids"] / nq}},
+        "gpu_launches": int(launches), "build_s": build_s, "generate_s": gen_s,
+        "visited_workspace_mb": stats["visited_workspace_bytes"] / 1e6,
+    }
+
+    # ---- the reference's CPU search on the same index (bounded sample) --------------------------------
+    if cpu:
+        out["cpu_baseline"] = cpu_leg(name, cfg, ix, q_host, gt, torch, dev, local_rank, args)
+    out["block_s"] = time.time() - t_block
+    return out, (sdk, ix)
+
+
+def cpu_leg(name, cfg, ix, q_host, gt, torch, dev, local_rank, args, sample_nq=None):
     from oracle import oracle as O
 
     threads = os.cpu_count() or 1
+    if not O.have_ref():
+        return {"value": None, "unit": "queries/s", "cores": threads, "kind": "port", "sample": "oracle/_ref is not built on this box; no CPU number"}
+    sub = None
+    folder = tempfile.mkdtemp(prefix="alaya_b200_bench_")
+    try:
+        if name == "c4":
+            # the reference would have to read 18 GB of files for the 5M set: its CPU number is taken on the first 1M
+            # rows (a smaller index is FASTER on the CPU, so this flatters the baseline, not us)
+            from alayalite_b200 import _cabi
+            from alayalite_b200.synthetic import low_rank_device
+
+            sub = 1_000_000
+            d_base, d_q = low_rank_device(sub, cfg["dim"], cfg["nq"], cfg["latent"], seed=42, normalize=cfg.get("normalize", False), device=dev)
+            _, ix, _ = make_index(cfg, d_base, local_rank)
+            gt_ids, _ = ground_truth(cfg, d_base, d_q, None, torch)
+            gt = gt_ids.cpu().numpy()
+            del d_base, gt_ids
+        t0 = time.time()
+        paths = save_for_reference(ix, folder, cfg["quant"])
+        save_s = time.time() - t0
+        nq_s = sample_nq or {"main": 10_000, "c2": 10_000, "c3": 1000, "c4": 500}.get(name, 2000)
+        qps, ef, rec, det = reference_on_files(cfg, paths, q_host, gt, threads, steps=3, warmup=1, sample_nq=nq_s, capacity=sub or cfg["n"])
+    finally:
+        shutil.rmtree(folder, ignore_errors=True)
+    rows = sub or cfg["n"]
+    return {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference", "ef": ef, "recall": rec,
+            "sample": f"3 passes of {det['nq']} queries at ef={ef} on {rows} x {cfg['dim']}" + (" (1M-row sub-sample of the 5M set)" if sub else "")
+                      + f"; unmodified reference (oracle/_ref), PyIndex::batch_search route (Scheduler + coroutines) on {threads} threads, simd {det['simd']}; "
+                      f"std::thread x search_solo gives {det['solo_qps']:.0f} q/s; graph built by ab_index_fit on the GPU and loaded through the reference's "
+                      f"Graph::load / RawSpace::load (save {save_s:.1f}s, load {det['load_s']:.1f}s)"}
+
+
+def bruteforce_block(args, torch, dev, stream, peaks):
+    """find_exact_gt / calc_gt on the tcgen05 path: 1M x 128 x 10k, top-10."""
+    from alayalite_b200 import _cabi
+    from alayalite_b200.synthetic import low_rank_device
+
+    n, dim, nq, k = 1_000_000, 128, 10_000, 10
+    d_base, d_q = low_rank_device(n, dim, nq, 16, seed=42, device=dev)
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        _cabi.bruteforce_topk_device("l2", d_base.data_ptr(), n, dim, d_q.data_ptr(), nq, k, d_ids.data_ptr(), d_dist.data_ptr(), stream)
+    torch.cuda.synchronize()
+    wall, dev_ms = [], []
+    l0 = _cabi.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(10):
+        t0 = time.perf_counter()
+        e0.record()
+        _cabi.bruteforce_topk_device("l2", d_base.data_ptr(), n, dim, d_q.data_ptr(), nq, k, d_ids.data_ptr(), d_dist.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
+        dev_ms.append(e0.elapsed_time(e1))
+    launches = (_cabi.kernel_launch_count() - l0) // 10
+    # exactness against float64 on a sample
+    sample = slice(0, 64)
+    ref = torch.cdist(d_q[sample].double(), d_base.double()).pow(2).topk(k, largest=False).indices.cpu().numpy()
+    exact = recall_at_k(d_ids[sample].cpu().numpy(), ref)
+    flops = 2.0 * nq * n * dim
+    _, bf16, src = peaks
+    tf32_peak = bf16 / 2
+    w, dm = float(np.median(wall)), float(np.median(dev_ms))
+    return {"workload": "exact top-10 of 10k queries over 1M x 128 fp32 (find_exact_gt / calc_gt), tcgen05 TF32 filter + exact fp32 refine",
+            "wall_ms": w, "device_ms": dm, "tflops_wall": flops / (w * 1e-3) / 1e12, "tflops_device": flops / (dm * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "achieved": flops / (dm * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s", "frac": flops / (dm * 1e-3) / 1e12 / tf32_peak,
+                         "peak_source": src + "; TF32 dense = bf16 / 2"},
+            "gpu_launches": int(launches), "ids_equal_float64_sample": exact}
+
+
+# --------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path, all host threads, on the main configuration."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    cfg = CONFIGS[args.config]
+    threads = os.cpu_count() or 1
     kind = "reference" if O.have_ref() else "port"
-    if kind == "port" and not os.path.exists(O.ORC_SO):
-        O.build(ref=False)
-    chk = O.Checker("ref" if kind == "reference" else "orc")
-    base, q = low_rank(N_BASE, DIM, NQ, LATENT, seed=42)
-    t0 = time.time()
-    if kind == "reference":
-        idx = chk.index("l2", "none", N_BASE, DIM)
-        idx.fit(base.copy(), EFC, threads)
-    else:  # the scalar port builds single-threaded: bound it to a 100k sample, labelled as such
-        base = base[:100_000]
-        idx = chk.index("l2", "none", base.shape[0], DIM)
-        idx.fit(base.copy(), EFC)
-    build_s = time.time() - t0
-    gt = chk.find_exact_gt(q[:500], base, TOPK, threads)  # reference's own exhaustive search, bounded sample
-    ef = None
-    for e in EF_SWEEP:
-        r = recall_at_k(idx.batch_search_inplace(q[:500], TOPK, e, threads), gt)
-        if r >= TARGET_RECALL:
-            ef, rec = e, r
-            break
-    if ef is None:
-        ef, rec = EF_SWEEP[-1], r
-    qc = np.ascontiguousarray(q)
-    for _ in range(args.warmup):
-        idx.batch_search_inplace(qc, TOPK, ef, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        idx.batch_search_inplace(qc, TOPK, ef, threads)
-    dt = time.perf_counter() - t0
-    qps = NQ * args.steps / dt
-    t0 = time.perf_counter()
-    idx.batch_search_inplace(qc, TOPK, ef, threads, solo=True)
-    solo_qps = NQ / (time.perf_counter() - t0)
-    sample = f"all {NQ} queries per step on {base.shape[0]} x {DIM}; index built by the reference on {threads} threads in {build_s:.1f}s; recall on 500 queries"
+    k, nq = cfg["topk"], cfg["nq"]
+    graph_note = ""
+    try:
+        import torch
+
+        have_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        have_gpu = False
+    if kind == "reference" and have_gpu and args.ref_build == "gpu":
+        from alayalite_b200 import _cabi
+        from alayalite_b200.synthetic import low_rank_device
+
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(0)
+        _cabi.check(_cabi.lib().ab_set_device(0))
+        d_base, d_q = low_rank_device(cfg["n"], cfg["dim"], nq, cfg["latent"], seed=42, normalize=cfg.get("normalize", False), device=dev)
+        _, ix, build_s = make_index(cfg, d_base, 0)
+        gt_ids, _ = ground_truth(cfg, d_base, d_q, None, torch)
+        gt = gt_ids.cpu().numpy()
+        q_host = d_q.cpu().numpy()
+        del d_base, gt_ids
+        folder = tempfile.mkdtemp(prefix="alaya_b200_ref_")
+        try:
+            paths = save_for_reference(ix, folder, cfg["quant"])
+            del ix
+            torch.cuda.empty_cache()
+            qps, ef, rec, det = reference_on_files(cfg, paths, q_host, gt, threads, args.steps, args.warmup, nq, cfg["n"])
+        finally:
+            shutil.rmtree(folder, ignore_errors=True)
+        graph_note = (f"rows, queries and exact ground truth generated on the GPU; graph built by ab_index_fit on the GPU in {build_s:.1f}s and loaded "
+                      f"through the reference's own Graph::load / RawSpace::load ({det['load_s']:.1f}s) because the reference's CPU build of {cfg['n']} rows "
+                      "takes minutes; the timed search is unmodified reference code")
+        ms, solo, simd = det["ms_per_step"], det["solo_qps"], det["simd"]
+    else:
+        # no GPU (or asked to): the reference builds its own index on a host-generated set, bounded to 1M rows
+        from alayalite_b200.synthetic import low_rank
+
+        n = min(cfg["n"], 1_000_000)
+        base, q_host = low_rank(n, cfg["dim"], nq, cfg["latent"], seed=42, normalize=cfg.get("normalize", False))
+        chk = O.Checker("ref" if kind == "reference" else "orc")
+        if kind != "reference":
+            base = base[:100_000]
+            n = len(base)
+        idx = chk.index(cfg["metric"], cfg["quant"], n, cfg["dim"])
+        t0 = time.time()
+        idx.fit(base.copy(), EFC, threads) if kind == "reference" else idx.fit(base.copy(), EFC)
+        build_s = time.time() - t0
+        gt = chk.find_exact_gt(q_host[:500], base, k, threads)
+        ef, rec = EF_SWEEP[-1], 0.0
+        for e in EF_SWEEP:
+            if e < k:
+                continue
+            rec = recall_at_k(idx.batch_search_inplace(q_host[:500], k, e, threads), gt)
+            if rec >= cfg["target"]:
+                ef = e
+                break
+        qc = np.ascontiguousarray(q_host)
+        for _ in range(args.warmup):
+            idx.batch_search_inplace(qc, k, ef, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            idx.batch_search_inplace(qc, k, ef, threads)
+        dt = time.perf_counter() - t0
+        qps, ms = nq * args.steps / dt, dt / args.steps * 1e3
+        solo, simd = None, chk.simd_level()
+        graph_note = f"index of {n} rows built by the {'reference' if kind == 'reference' else 'oracle port'} on {threads} threads in {build_s:.1f}s (host-generated rows)"
+    sample = f"all {nq} queries per step at ef={ef} (recall@{k}={rec:.4f}) on {cfg['n']} x {cfg['dim']}; {graph_note}"
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "ef": ef, "recall_at_10": rec, "path": "PyIndex::batch_search (Scheduler + coroutines) via oracle/_ref" if kind == "reference" else "oracle port",
-                   "simd": chk.simd_level(), "search_solo_threads_qps": solo_qps},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "ef": ef, "recall_at_10": rec,
+                   "path": "PyIndex::batch_search (Scheduler + coroutines) via oracle/_ref" if kind == "reference" else "oracle port",
+                   "simd": simd, "search_solo_threads_qps": solo},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(base, q, gt, threads):
-    """Reference CPU path on the box's host cores, bounded: one index build + a few query passes."""
-    from oracle import oracle as O
-
-    kind = "reference" if O.have_ref() else "port"
-    if kind == "port" and not os.path.exists(O.ORC_SO):
-        O.build(ref=False)
-    chk = O.Checker("ref" if kind == "reference" else "orc")
-    t0 = time.time()
-    if kind == "reference":
-        idx = chk.index("l2", "none", base.shape[0], DIM)
-        idx.fit(base.copy(), EFC, threads)
-    else:
-        base = base[:100_000]
-        idx = chk.index("l2", "none", base.shape[0], DIM)
-        idx.fit(base.copy(), EFC)
-        gt = None
-    build_s = time.time() - t0
-    ef, rec = EF_SWEEP[-1], None
-    if gt is not None:
-        for e in EF_SWEEP:
-            rec = recall_at_k(idx.batch_search_inplace(q[:1000], TOPK, e, threads), gt[:1000])
-            if rec >= TARGET_RECALL:
-                ef = e
-                break
-    else:
-        ef = 50
-    qc = np.ascontiguousarray(q)
-    idx.batch_search_inplace(qc, TOPK, ef, threads)
-    reps = 3
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        idx.batch_search_inplace(qc, TOPK, ef, threads)
-    qps = NQ * reps / (time.perf_counter() - t0)
-    t0 = time.perf_counter()
-    idx.batch_search_inplace(qc, TOPK, ef, threads, solo=True)
-    solo = NQ / (time.perf_counter() - t0)
-    return {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind,
-            "sample": f"{reps} passes of {NQ} queries at ef={ef} (recall@10={rec}) on {base.shape[0]} x {DIM}; reference index built on {threads} threads in {build_s:.1f}s; "
-                      f"PyIndex::batch_search route (Scheduler+coroutines); std::thread x search_solo gives {solo:.0f} q/s; simd {chk.simd_level()}"}
-
-
 # --------------------------------------------------------------------------------------------------
-def ours_arm(args, rank, world, local_rank):
+def ours_single(args, local_rank):
     import torch
 
     from alayalite_b200 import _cabi
-    from alayalite_b200.synthetic import low_rank
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _cabi.check(_cabi.lib().ab_set_device(local_rank))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-
-    # ---- data: every rank owns one shard (same generator, independent stream per rank); queries are shared ---------------------
-    base, q = low_rank(N_BASE, DIM, NQ, LATENT, seed=42, shard=rank)  # same distribution and queries on every rank
-    qt = torch.from_numpy(q).pin_memory()
-    d_q = qt.to(dev)
-    if world > 1:
-        dist.broadcast(d_q, 0)
-        qt.copy_(d_q)
-        q = qt.numpy()
-    id_offset = rank * N_BASE
-
-    # ---- build (untimed part of the step, reported) ----------------------------------------------
-    ix = _cabi.NativeIndex("l2", "none", N_BASE, device=local_rank)
-    t0 = time.time()
-    cache = os.path.join(args.index_cache, f"rank{rank}") if args.index_cache else None
-    if cache and os.path.exists(os.path.join(cache, "hnsw.index")):
-        # profiling aid: reuse an index this same script built and saved (reference file format)
-        ix.load(os.path.join(cache, "hnsw.index"), os.path.join(cache, "raw.data"))
-        built = "loaded from --index-cache"
-    else:
-        ix.fit(base, EFC)
-        built = "ab_index_fit on the GPU"
-        if cache:
-            os.makedirs(cache, exist_ok=True)
-            ix.save(os.path.join(cache, "hnsw.index"), os.path.join(cache, "raw.data"))
-    build_s = time.time() - t0
-    # a real (non-null) stream shared by torch's events/collectives and the library's kernels
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
+    peaks = load_peaks()
+    budget = Budget(args.budget)
+    blocks = [b for b in args.blocks.split(",") if b]
 
-    from alayalite_b200.sharded import ShardedIndex
-
-    sh = ShardedIndex(ix, id_offset, world)
-    buf = sh._buffers(NQ, TOPK, dev)
-    d_ids, d_dist = buf["ids"], buf["dist"]
-
-    # ---- exact ground truth on the GPU (brute force per shard, merged across shards) --------------
-    d_base = torch.from_numpy(base).to(dev)
-    _cabi.bruteforce_topk_device("l2", d_base.data_ptr(), N_BASE, DIM, d_q.data_ptr(), NQ, TOPK, d_ids.data_ptr(), d_dist.data_ptr(), stream)
-    d_ids += id_offset
-    gt = sh.exchange(d_ids, d_dist, buf, stream)[0].cpu().numpy().copy()
-    del d_base
+    clocks = ClockSampler(local_rank)
+    main, keep = run_block(args.config, CONFIGS[args.config], args, torch, dev, local_rank, stream, peaks, cpu=not args.no_cpu_baseline, clocks=clocks)
+    del keep
     torch.cuda.empty_cache()
-
-    # ---- operating point: smallest ef with recall@10 >= 0.95 -------------------------------------
-    ef, rec = EF_SWEEP[-1], 0.0
-    for e in EF_SWEEP:
-        rec = recall_at_k(sh.batch_search_device(d_q, TOPK, e, stream)[0].cpu().numpy(), gt)
-        if rec >= TARGET_RECALL:
-            ef = e
-            break
-
-    # ---- timed region: K steps, device events, L2 flushed between steps ---------------------------
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    for _ in range(max(args.warmup, 3)):
-        sh.batch_search_device(d_q, TOPK, ef, stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = _cabi.kernel_launch_count()
-    times, kernel_times = [], []
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    with ClockSampler(local_rank) as clocks:
-        torch.cuda.synchronize()
-        for _ in range(args.steps):
-            flush.zero_()
-            ev[0].record()
-            if world == 1:
-                ix.batch_search_device(d_q.data_ptr(), NQ, TOPK, ef, d_ids.data_ptr(), d_dist.data_ptr(), True, stream)
-                ev[1].record()
-            else:  # search (storing into every rank's gather buffer) + barrier + merge
-                sh.batch_search_device(d_q, TOPK, ef, stream, after_search=ev[1].record)
-            ev[2].record()
-            torch.cuda.synchronize()
-            kernel_times.append(ev[0].elapsed_time(ev[1]))
-            times.append(ev[0].elapsed_time(ev[2]))
-    launches = _cabi.kernel_launch_count() - launches0
-    if world > 1:
-        dist.barrier()
-    total_ms = float(sum(times))
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    stats = ix.stats()
-
-    # ---- e2e: host buffers in, host ids out, copies inside the timed region ------------------------
-    # N = 1: the reference-facing C-ABI call ab_index_batch_search on pinned host memory.
-    # N > 1: ShardedIndex.batch_search (H2D queries, search, all-gather + merge, D2H merged ids).
-    h_ids = torch.empty((NQ, TOPK), dtype=torch.int32).pin_memory()
-
-    def e2e_step():
-        if world == 1:
-            ix.batch_search_ptr(qt.data_ptr(), NQ, TOPK, ef, h_ids.data_ptr())
-        else:
-            sh.batch_search(qt, TOPK, ef, out=h_ids, device=dev, stream=stream)
-
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_recall = recall_at_k(h_ids.numpy(), gt)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (beam_search_kernel): algorithmic bytes / device time -----
-    row_bytes = DIM * 4
-    alg_bytes = (stats["ndc"] + stats["overlay"]) * row_bytes + stats["hops"] * 128  # per launch (SURVEY.md 8d)
-    k_ms = float(np.mean(kernel_times))
-    peak, peak_src = load_peaks()
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = load_traffic()
-    units = NQ * world * args.steps
-    value = units / (total_ms * 1e-3)
+    cfg = CONFIGS[args.config]
     line = {
-        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "ef": ef, "recall_at_10": rec, "vectors_total": N_BASE * world, "shards": world, "exchange": sh.exchange_kind,
-                   "timing": "CUDA events per step on the launching stream; 256 MB L2 flush between steps; index 640 MB > 126 MB L2",
-                   "build_s": build_s, "index": built, "unit_note": "value counts (query, shard) searches; merged_qps is the end-user rate" if world > 1 else "1 shard: value == merged_qps"},
-        "merged_qps": NQ * args.steps / (total_ms * 1e-3),
-        "e2e": {"value": NQ * world * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * TOPK * 4,
-                "api": "ab_index_batch_search (C ABI, pinned host buffers)" if world == 1 else "ShardedIndex.batch_search (pinned host buffers)", "recall_at_10": e2e_recall},
-        "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "beam_search_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                     "per_query": {"ndc_level0": stats["ndc"] / NQ, "ndc_overlay": stats["overlay"] / NQ, "hops": stats["hops"] / NQ, "bytes": alg_bytes / NQ}},
+        "metric": METRIC, "value": main["value"], "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "ef": main["ef"], "recall_at_10": main["recall"], "vectors_total": cfg["n"], "shards": 1, "replicas": 1,
+                   "timing": "CUDA events per step on the launching stream; 256 MB L2 flush between steps; index larger than the 126 MB L2",
+                   "build_s": main["build_s"], "index": "ab_index_fit on the GPU from device-resident rows", "recall_by_ef": main["recall_by_ef"]},
+        "merged_qps": main["value"],
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": clocks.summary(), "roofline": main["roofline"],
+        "visited_workspace_mb": main["visited_workspace_mb"],
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(base, q, gt, os.cpu_count() or 1)
+    if "cpu_baseline" in main:
+        line["cpu_baseline"] = main["cpu_baseline"]
+    for b in blocks:
+        if b == "main":
+            continue
+        need = {"c2": 25, "bf": 10, "c3": 45, "c4": 110}.get(b, 30)
+        if budget.left() < need:
+            line[{"bf": "bruteforce"}.get(b, b)] = {"skipped": f"time budget ({args.budget}s) would be overrun; run with --blocks {b} --budget 600"}
+            continue
+        try:
+            if b == "bf":
+                line["bruteforce"] = bruteforce_block(args, torch, dev, stream, peaks)
+            else:
+                blk, keep = run_block(b, CONFIGS[b], args, torch, dev, local_rank, stream, peaks, cpu=not args.no_cpu_baseline)
+                del keep
+                line[b] = blk
+        except Exception as e:  # noqa: BLE001  (an extra block must not take the headline down with it)
+            line[{"bf": "bruteforce"}.get(b, b)] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    line["bench_s"] = time.time() - budget.t0
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -380,16 +568,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="main", choices=list(CONFIGS), help="workload of the headline numbers")
+    ap.add_argument("--blocks", default="c2,bf,c3,c4", help="extra blocks of the N=1 line, run while the time budget lasts")
+    ap.add_argument("--budget", type=float, default=200.0, help="seconds after which no further extra block is started")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--index-cache", default="", help="directory to save/load the built index (profiling aid)")
+    ap.add_argument("--ref-build", default="gpu", choices=["gpu", "own"], help="--impl reference: whose graph the reference searches")
+    ap.add_argument("--layout", default="", help="N>1: SxR = id-range shards x query replicas (default 1xN)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+    elif world == 1:
+        ours_single(args, local_rank)
     else:
-        ours_arm(args, rank, world, local_rank)
+        from bench_multi import ours_multi
+
+        ours_multi(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -68,7 +68,8 @@ void ab_index_destroy(ab_index *index);
 
 /* PyIndex::fit (index.hpp:177-227): copy rows to the device (COS: L2-normalise the device copy;
  * the caller's buffer is NOT modified, unlike raw_space.hpp:131-139), fit + encode the SQ space,
- * build the HNSW graph on the GPU. num_threads is accepted for API compatibility and ignored. */
+ * build the HNSW graph on the GPU. num_threads is accepted for API compatibility and ignored.
+ * `data` may also be device memory on the index's device (rows generated or already resident there). */
 int ab_index_fit(ab_index *index, const float *data, uint64_t n, uint32_t dim,
                  uint32_t ef_construction, uint32_t num_threads);
 
@@ -115,16 +116,6 @@ int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64
                                  uint32_t ef, int32_t rerank, uint32_t *d_out_ids, float *d_out_dist,
                                  void *stream);
 
-/* Multi-GPU (no counterpart in the reference): the same search, whose kernel additionally stores
- * every final (id + id_offset, distance) into slot `slot` of n_dest gather buffers laid out [slots, nq, topk]
- * -- dest_ids / dest_dist are HOST arrays of n_dest (<= 16) device addresses, normally one buffer per rank of
- * the box mapped into this process as peer memory -- so the shard exchange rides on the search itself and
- * only a barrier + ab_merge_topk_device remain. d_out_ids / d_out_dist receive the local lists as usual. */
-int ab_index_batch_search_scatter_device(ab_index *index, const float *d_queries, uint64_t nq, uint32_t topk,
-                                         uint32_t ef, int32_t rerank, uint32_t *d_out_ids, float *d_out_dist,
-                                         uint32_t id_offset, uint32_t slot, uint32_t n_dest,
-                                         const uint64_t *dest_ids, const uint64_t *dest_dist, void *stream);
-
 /* Parity / interchange hooks: split fit into "spaces" and "graph" so that a graph built elsewhere
  * (the reference on the CPU) can be searched on the GPU and vice versa.                          */
 int ab_index_fit_spaces(ab_index *index, const float *data, uint64_t n, uint32_t dim);
@@ -139,9 +130,14 @@ int ab_index_get_graph(ab_index *index, uint32_t *adj, uint32_t *levels, uint32_
 /* SQ codes [n, row_bytes] (row_bytes = dim for SQ8, (dim+1)/2 for SQ4) and quantizer min/max [dim] */
 int ab_index_get_codes(ab_index *index, uint8_t *codes, float *min, float *max);
 /* Counters of the last batch search: {level-0 distance evaluations, expanded nodes (hops),
- * overlay distance evaluations, queries re-run through the exact global-bitmap visited set,
+ * overlay distance evaluations, queries whose visited set continued in the global overflow table,
  * queries} -- feeds the algorithmic-bytes figure of the roofline. */
 int ab_index_search_stats(ab_index *index, uint64_t stats[5]);
+/* The same counters, extended: stats[0..4] as above, stats[5] = queries that went past the per-warp overflow
+ * table into a pooled bitmap, stats[6] = ids stored in overflow tables, stats[7] = bytes of global memory the
+ * visited-set workspace holds (it follows ef and the number of resident warps, not the number of rows).
+ * Writes min(count, 8) values, zero beyond. */
+int ab_index_search_stats_ex(ab_index *index, uint64_t *stats, uint32_t count);
 /* Search-space pool of one batch, before re-rank: pool_ids/pool_dist [nq, ef], sizes [nq].      */
 int ab_index_batch_traverse(ab_index *index, const float *queries, uint64_t nq, uint32_t ef,
                             uint32_t *pool_ids, float *pool_dist, uint32_t *pool_sizes);
@@ -173,6 +169,60 @@ int ab_bruteforce_topk_device(int32_t metric, const float *d_data, uint64_t n, u
  * laid out [lists, nq, k] (already carrying global ids) into [nq, k] by (distance, id). */
 int ab_merge_topk_device(const float *d_dist, const uint32_t *d_ids, uint32_t lists, uint64_t nq,
                          uint32_t k, uint32_t *d_out_ids, float *d_out_dist, void *stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Multi-GPU (no counterpart in the reference): one logical index split by contiguous id ranges   */
+/* over S GPUs ("shards"), optionally R query replicas of that. Shard s owns rows                               */
+/* [s * ceil(n/S), min(n, (s+1) * ceil(n/S))) with local ids, every shard answers every query of its replica    */
+/* group, and the per-shard top-k lists are folded into one by (distance, global id). The exchange is fused     */
+/* into the search: the kernel that produces a query's final list stores it into the mailbox of the query's     */
+/* owner shard (peer memory over NVLink) and the last shard to arrive merges -- no collective, no barrier, no   */
+/* merge kernel (csrc/exchange.cuh). SQ spaces must be fitted with the GLOBAL quantiser range so that sharded   */
+/* codes equal the codes of the single index.                                                                   */
+
+/* Per-dimension min / max of rows the way SQ8Quantizer::fit sees them (sq8.hpp:99-118; rows L2-normalised first
+ * for AB_METRIC_COS because the reference fits its SQ space on the normalised buffer, index.hpp:197-206).
+ * `data` may be host or device memory. Combine the per-shard results with min / max and pass them to
+ * ab_index_fit_ranged. */
+int ab_quant_minmax(int32_t metric, const float *data, uint64_t n, uint32_t dim, float *min, float *max);
+/* ab_index_fit with a given quantiser range (min / max [dim], both NULL = fit on these rows as usual). */
+int ab_index_fit_ranged(ab_index *index, const float *data, uint64_t n, uint32_t dim, uint32_t ef_construction,
+                        const float *min, const float *max);
+
+/* (a) One process drives the whole S x R grid (what the reference's single-process pybind host needs).
+ * devices: n_shards * n_replicas CUDA ordinals, replica-major (the shards of replica 0 first); an ordinal may
+ * repeat. params->capacity is the capacity of the LOGICAL index. fit builds all shard graphs concurrently;
+ * batch_search splits the queries over the replicas, ids are global row numbers of `data`. Pinned + mapped
+ * caller buffers are read / written in place by the kernels of every GPU. out_dist may be NULL. */
+typedef struct ab_group ab_group;
+int ab_group_create(const ab_params *params, const int32_t *devices, uint32_t n_shards, uint32_t n_replicas, ab_group **out);
+void ab_group_destroy(ab_group *group);
+int ab_group_fit(ab_group *group, const float *data, uint64_t n, uint32_t dim, uint32_t ef_construction);
+int ab_group_batch_search(ab_group *group, const float *queries, uint64_t nq, uint32_t topk, uint32_t ef,
+                          uint32_t *out_ids, float *out_dist);
+/* the ab_index of one shard (owned by the group) */
+int ab_group_index(ab_group *group, uint32_t shard, uint32_t replica, ab_index **out);
+
+/* (b) One process per GPU (torchrun, MPI ...): every rank of a replica group creates a communicator around its
+ * fitted shard and publishes `handle` (AB_COMM_HANDLE_BYTES opaque bytes: a CUDA IPC handle of the rank's mailbox);
+ * the caller gathers the handles of ranks 0..world-1 in rank order with whatever transport it has and every rank
+ * connects. max_nq / max_topk bound later calls and must be equal on all ranks.
+ * ab_comm_batch_search_device: d_queries [nq, dim] on this rank's device (the same queries on every rank of the
+ * group); asynchronous on `stream`. This rank OWNS queries rank, rank + world, ...: their merged lists (global ids
+ * = local id + id_offset of the shard that holds the row) arrive in d_out_ids / d_out_dist as
+ * [ceil((nq - rank) / world), topk] rows, in that order. Buffers may be device or pinned host memory;
+ * d_out_dist may be NULL. Every rank must make the same sequence of calls; two communicators must not share one
+ * stream. */
+#define AB_COMM_HANDLE_BYTES 128
+typedef struct ab_comm ab_comm;
+int ab_comm_create(ab_index *local, uint32_t rank, uint32_t world, uint32_t id_offset, uint64_t max_nq,
+                   uint32_t max_topk, ab_comm **out, uint8_t *handle);
+int ab_comm_connect(ab_comm *comm, const uint8_t *handles);
+int ab_comm_batch_search_device(ab_comm *comm, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef,
+                                uint32_t *d_out_ids, float *d_out_dist, void *stream);
+/* number of calls whose wait for the peers timed out (a peer that never searched); 0 = healthy */
+int ab_comm_errors(ab_comm *comm, uint32_t *out);
+void ab_comm_destroy(ab_comm *comm);
 
 /* Launch plan the traversal would use (host-side decision only, no device needed): for quantization / row
  * length in 16-byte chunks / ef / batch size / rows in the index on a device with `sm_count` SMs and

@@ -37,5 +37,5 @@ with torch.cuda.stream(stream):
         rec = np.mean([len(set(ids[i]) & set(gt[i])) / k for i in range(nq)])
         st = ix.stats()
         bq = ((st["ndc"] + st["overlay"]) * row + st["hops"] * 128 + (k * dim * 4 if a.quant != "none" else 0)) / nq
-        ms = float(np.mean(ts))
-        print(f"ef={ef:4d} {ms:7.3f} ms  qps={nq/ms*1e3:10.0f} recall@{k}={rec:.4f} B/q={bq/1e3:6.1f}KB alg={nq/ms*1e3*bq/1e12:5.2f} TB/s frac={nq/ms*1e3*bq/6555.8e9:.3f} bitmap={st['spilled']}", flush=True)
+        ms = float(np.median(ts))
+        print(f"ef={ef:4d} {ms:7.3f} ms (min {min(ts):.3f} max {max(ts):.3f}) ovf_ids/q={st['overflow_ids']/nq:.0f} big={st['bitmap']}  qps={nq/ms*1e3:10.0f} recall@{k}={rec:.4f} B/q={bq/1e3:6.1f}KB alg={nq/ms*1e3*bq/1e12:5.2f} TB/s frac={nq/ms*1e3*bq/6555.8e9:.3f} bitmap={st['spilled']}", flush=True)
