@@ -53,6 +53,8 @@ def lib():
         _lib.ab_index_get_dim.argtypes = [C.c_void_p]
         _lib.ab_index_get_size.argtypes = [C.c_void_p]
         _lib.ab_index_destroy.argtypes = [C.c_void_p]
+        _lib.ab_group_destroy.argtypes = [C.c_void_p]
+        _lib.ab_comm_destroy.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -202,16 +204,6 @@ class NativeIndex:
         check(lib().ab_index_batch_search_device(self.h, _vp(d_queries), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef), C.c_int32(int(rerank)),
                                                  _vp(d_out_ids), _vp(d_out_dist), _vp(stream)))
 
-    def batch_search_scatter_device(self, d_queries, nq, topk, ef, d_out_ids, d_out_dist, id_offset, slot, dest_ids, dest_dist,
-                                    rerank=True, stream=None):
-        """dest_ids / dest_dist: device addresses of the [slots, nq, topk] gather buffers (one per rank, peer mapped)."""
-        n = len(dest_ids)
-        a_ids = (C.c_uint64 * n)(*[int(x) for x in dest_ids])
-        a_dist = (C.c_uint64 * n)(*[int(x) for x in dest_dist])
-        check(lib().ab_index_batch_search_scatter_device(self.h, _vp(d_queries), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef),
-                                                         C.c_int32(int(rerank)), _vp(d_out_ids), _vp(d_out_dist), C.c_uint32(id_offset),
-                                                         C.c_uint32(slot), C.c_uint32(n), a_ids, a_dist, _vp(stream)))
-
     def traverse(self, queries, ef):
         q = _f32(queries)
         nq = q.shape[0]
@@ -289,3 +281,117 @@ def bruteforce_topk_device(metric, d_data, n, dim, d_queries, nq, k, d_out_ids, 
 
 def merge_topk_device(d_dist, d_ids, lists, nq, k, d_out_ids, d_out_dist=None, stream=None):
     check(lib().ab_merge_topk_device(_vp(d_dist), _vp(d_ids), C.c_uint32(lists), C.c_uint64(nq), C.c_uint32(k), _vp(d_out_ids), _vp(d_out_dist), _vp(stream)))
+
+
+# ---- multi-GPU (include/alaya_b200.h "Multi-GPU") -------------------------------------------------------
+COMM_HANDLE_BYTES = 128
+
+
+def quant_minmax(metric, data):
+    """Per-dimension (min, max) of `data` the way the SQ quantiser sees the rows (COS: normalised first)."""
+    d = _f32(data)
+    mn, mx = np.zeros(d.shape[1], np.float32), np.zeros(d.shape[1], np.float32)
+    check(lib().ab_quant_minmax(C.c_int32(METRICS[metric]), _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]), _p(mn, f32p), _p(mx, f32p)))
+    return mn, mx
+
+
+def quant_minmax_ptr(metric, ptr, n, dim):
+    mn, mx = np.zeros(dim, np.float32), np.zeros(dim, np.float32)
+    check(lib().ab_quant_minmax(C.c_int32(METRICS[metric]), C.cast(_vp(ptr), f32p), C.c_uint64(n), C.c_uint32(dim), _p(mn, f32p), _p(mx, f32p)))
+    return mn, mx
+
+
+def fit_ranged(index: NativeIndex, data_or_ptr, n=None, dim=None, ef_construction=100, mn=None, mx=None):
+    """ab_index_fit with a given quantiser range (shards of one logical index share the global range)."""
+    if n is None:
+        d = _f32(data_or_ptr)
+        ptr, n, dim = _p(d, f32p), d.shape[0], d.shape[1]
+    else:
+        ptr = C.cast(_vp(data_or_ptr), f32p)
+    pmn = _p(_f32(mn), f32p) if mn is not None else None
+    pmx = _p(_f32(mx), f32p) if mx is not None else None
+    check(lib().ab_index_fit_ranged(index.h, ptr, C.c_uint64(n), C.c_uint32(dim), C.c_uint32(ef_construction), pmn, pmx))
+
+
+class Group:
+    """ab_group: a shards x replicas grid of GPUs driven by this process."""
+
+    def __init__(self, metric="l2", quant="none", capacity=100000, devices=(0,), n_shards=1, n_replicas=1, index_type="hnsw"):
+        self.metric, self.quant, self.n_shards, self.n_replicas = metric, quant, n_shards, n_replicas
+        assert len(devices) == n_shards * n_replicas
+        p = Params(INDEX_TYPES[index_type], QUANTS[quant], METRICS[metric], capacity, 32, -1)
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        check(lib().ab_group_create(C.byref(p), devs, C.c_uint32(n_shards), C.c_uint32(n_replicas), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            try:
+                lib().ab_group_destroy(self.h)
+            except TypeError:
+                pass
+            self.h = None
+
+    def fit(self, data, ef_construction=100):
+        d = _f32(data)
+        check(lib().ab_group_fit(self.h, _p(d, f32p), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]), C.c_uint32(ef_construction)))
+
+    def batch_search(self, queries, topk, ef=100, with_distance=False):
+        q = _f32(queries)
+        ids = np.zeros((q.shape[0], topk), np.uint32)
+        dist = np.zeros((q.shape[0], topk), np.float32) if with_distance else None
+        check(lib().ab_group_batch_search(self.h, _p(q, f32p), C.c_uint64(q.shape[0]), C.c_uint32(topk), C.c_uint32(ef), _p(ids, u32p),
+                                          _p(dist, f32p) if with_distance else None))
+        return (ids, dist) if with_distance else ids
+
+    def batch_search_ptr(self, q_ptr, nq, topk, ef, ids_ptr, dist_ptr=None):
+        check(lib().ab_group_batch_search(self.h, C.cast(_vp(q_ptr), f32p), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef),
+                                          C.cast(_vp(ids_ptr), u32p), C.cast(_vp(dist_ptr), f32p) if dist_ptr else None))
+
+    def shard(self, shard=0, replica=0):
+        """The ab_index of one shard (owned by the group)."""
+        h = C.c_void_p()
+        check(lib().ab_group_index(self.h, C.c_uint32(shard), C.c_uint32(replica), C.byref(h)))
+        return NativeIndex(self.metric, self.quant, 0, handle=h.value)
+
+
+class Comm:
+    """ab_comm: this process's shard of a replica group (one process per GPU)."""
+
+    def __init__(self, index: NativeIndex, rank, world, id_offset, max_nq, max_topk):
+        self.index, self.rank, self.world = index, rank, world
+        buf = (C.c_uint8 * COMM_HANDLE_BYTES)()
+        h = C.c_void_p()
+        check(lib().ab_comm_create(index.h, C.c_uint32(rank), C.c_uint32(world), C.c_uint32(id_offset), C.c_uint64(max_nq), C.c_uint32(max_topk),
+                                   C.byref(h), buf))
+        self.h, self.handle = h, bytes(buf)
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == self.world * COMM_HANDLE_BYTES
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().ab_comm_connect(self.h, arr))
+
+    def owned(self, nq):
+        return (nq - self.rank + self.world - 1) // self.world if nq > self.rank else 0
+
+    def batch_search_device(self, d_queries, nq, topk, ef, d_out_ids, d_out_dist=None, stream=None):
+        check(lib().ab_comm_batch_search_device(self.h, _vp(d_queries), C.c_uint64(nq), C.c_uint32(topk), C.c_uint32(ef), _vp(d_out_ids),
+                                                _vp(d_out_dist), _vp(stream)))
+
+    def errors(self):
+        out = C.c_uint32(0)
+        check(lib().ab_comm_errors(self.h, C.byref(out)))
+        return int(out.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ab_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except TypeError:
+            pass

@@ -193,7 +193,7 @@ void index_mark_workspace_use(ab_index *ix, cudaStream_t stream) {
 
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange) {
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange, bool pad_empty) {
   AB_CHECK(ix->has_graph, AB_ERR_STATE, "index is not fitted or loaded");
   AB_CHECK(topk >= 1 && ef >= 1, AB_ERR_INVALID, "topk and ef must be positive");
   // the reference reads uninitialised pool slots when topk > ef (SURVEY.md 8b "Errors"); rejected here
@@ -274,7 +274,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   ix->w_visited.fill(a);
   a.stats = ix->w_stats.p;
   if (exch_in_search) a.exchange = *exchange;
-  a.pad_empty = (exchange != nullptr && need_rerank) ? 1 : 0;
+  a.pad_empty = ((exchange != nullptr && need_rerank) || pad_empty) ? 1 : 0;
   launch_search(quant, plan, a, stream);
   ix->last_ef = ef;
   ix->last_nq = nq;
@@ -296,6 +296,7 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
     r.out_ids = d_out_ids;
     r.out_dist = d_out_dist;
     if (exchange != nullptr) r.exchange = *exchange;
+    r.no_zero_fill = (exchange != nullptr || pad_empty) ? 1 : 0;
     launch_rerank(r, ix->sm_count, stream);
   }
   index_mark_workspace_use(ix, stream);
@@ -577,7 +578,8 @@ int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64
     std::lock_guard<std::mutex> lock(index->mu);
     use_device(index);
     cudaStream_t s = static_cast<cudaStream_t>(stream);  // NULL = the legacy default stream, ordered with the caller's work
-    index_search_device(index, d_queries, nq, topk, ef, rerank != 0, d_out_ids, d_out_dist, nullptr, nullptr, nullptr, s);
+    index_search_device(index, d_queries, nq, topk, ef, (rerank & 1) != 0, d_out_ids, d_out_dist, nullptr, nullptr, nullptr, s, nullptr,
+                        (rerank & 2) != 0);
   });
 }
 

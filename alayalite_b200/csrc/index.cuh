@@ -90,7 +90,7 @@ uint64_t index_lists_len(const ab_index *ix);
 // d_queries / outputs are device pointers. cand/pool outputs optional.
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange = nullptr);
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange = nullptr, bool pad_empty = false);
 void index_save(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_load(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_build_graph(ab_index *ix, uint32_t ef_construction);

@@ -20,7 +20,7 @@ namespace {
 // PyIndex::rerank (python/include/index.hpp:450-467): exact raw-space distance for the ef entries of
 // res_pool -- the topk ids search wrote plus (ef - topk) untouched zeros -- ordered by (dist, id).
 __host__ __device__ inline size_t rerank_warp_bytes(const RerankArgs &a) {
-  const uint32_t nz = a.exchange.n_shards > 0 ? 0u : (a.ef - a.topk < a.topk ? a.ef - a.topk : a.topk);
+  const uint32_t nz = a.no_zero_fill ? 0u : (a.ef - a.topk < a.topk ? a.ef - a.topk : a.topk);
   const size_t own = size_t(a.nchunks) * 16 + round_up16(size_t(a.topk + nz) * 4) * 2;
   const size_t scratch = round_up16(size_t(a.exchange.n_shards) * a.topk * 8);
   return own > scratch ? own : scratch;
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankArgs a) {
   const int warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
   const size_t q_bytes = size_t(a.nchunks) * 16;
-  // copies of id 0 that can reach the output (none when the lists feed a shard exchange: padding is not a row)
-  const uint32_t nz = a.exchange.n_shards > 0 ? 0u : min(a.ef - a.topk, a.topk);
+  // copies of id 0 that can reach the output (none when the lists feed a shard merge: padding is not a row)
+  const uint32_t nz = a.no_zero_fill ? 0u : min(a.ef - a.topk, a.topk);
   const uint32_t L = a.topk + nz;
   const size_t per_warp = rerank_warp_bytes(a);
   uint8_t *wbase = smem + size_t(warp) * per_warp;

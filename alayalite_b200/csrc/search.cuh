@@ -81,7 +81,9 @@ struct RerankArgs {
   const uint32_t *cand_ids;  // [nq, topk] search-space top-k
   uint32_t *out_ids;         // [nq, topk]
   float *out_dist;           // [nq, topk] or null
-  Exchange exchange;         // n_shards > 0: no zero-fill quirk (only the topk real candidates are re-ranked), lists delivered
+  Exchange exchange;         // n_shards > 0: lists delivered to the owner shards
+  int no_zero_fill;          // per-shard lists that will be merged: only the topk real candidates are re-ranked (the
+                             // reference's (ef - topk) zero slots would put row 0 of every shard into the merge)
 };
 
 // Launch configuration chosen on the host (search.cu)

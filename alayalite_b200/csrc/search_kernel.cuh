@@ -773,8 +773,11 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     for (uint32_t i = lane; i < a.topk; i += 32) {
       const bool in = i <= a.ef;  // slots past the pool size are zero, like the reference's pool
       uint32_t rid = in ? (ws.pool[i].y & kIdMask) : 0u;
-      const float rd = in ? __uint_as_float(ws.pool[i].x) : 0.f;
-      if (a.pad_empty && static_cast<int>(i) >= size) rid = kEmptyId;
+      float rd = in ? __uint_as_float(ws.pool[i].x) : 0.f;
+      if (a.pad_empty && static_cast<int>(i) >= size) {
+        rid = kEmptyId;
+        rd = FLT_MAX;
+      }
       a.out_ids[size_t(qi) * a.topk + i] = rid;
       if (a.out_dist) a.out_dist[size_t(qi) * a.topk + i] = rd;
     }

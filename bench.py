@@ -48,7 +48,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "batch_search QPS at recall@10>=0.95"
 EFC = 100
-EF_SWEEP = (10, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 90, 100, 116, 128, 144, 160, 180, 200, 240, 280, 340, 400, 500, 640, 800)
+EF_SWEEP = (10, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 68, 72, 76, 80, 90, 100, 116, 128, 144, 160, 180, 200, 240, 280, 340, 400, 500, 640, 800)
 
 # name -> workload. `latent` is the rank of the generator; SQ configs are calibrated so that the
 # operating point lands at ef 50-200 like the survey asks.
@@ -359,7 +359,7 @@ def cpu_leg(name, cfg, ix, q_host, gt, torch, dev, local_rank, args, sample_nq=N
 
             sub = 1_000_000
             d_base, d_q = low_rank_device(sub, cfg["dim"], cfg["nq"], cfg["latent"], seed=42, normalize=cfg.get("normalize", False), device=dev)
-            _, ix, _ = make_index(cfg, d_base, local_rank)
+            sdk_sub, ix, _ = make_index(cfg, d_base, local_rank)  # sdk_sub owns the handle: keep it alive
             gt_ids, _ = ground_truth(cfg, d_base, d_q, None, torch)
             gt = gt_ids.cpu().numpy()
             del d_base, gt_ids
@@ -443,7 +443,7 @@ def reference_arm(args, rank, world):
         torch.cuda.set_device(0)
         _cabi.check(_cabi.lib().ab_set_device(0))
         d_base, d_q = low_rank_device(cfg["n"], cfg["dim"], nq, cfg["latent"], seed=42, normalize=cfg.get("normalize", False), device=dev)
-        _, ix, build_s = make_index(cfg, d_base, 0)
+        sdk_ref, ix, build_s = make_index(cfg, d_base, 0)  # sdk_ref owns the handle
         gt_ids, _ = ground_truth(cfg, d_base, d_q, None, torch)
         gt = gt_ids.cpu().numpy()
         q_host = d_q.cpu().numpy()
@@ -451,7 +451,7 @@ def reference_arm(args, rank, world):
         folder = tempfile.mkdtemp(prefix="alaya_b200_ref_")
         try:
             paths = save_for_reference(ix, folder, cfg["quant"])
-            del ix
+            del ix, sdk_ref
             torch.cuda.empty_cache()
             qps, ef, rec, det = reference_on_files(cfg, paths, q_host, gt, threads, args.steps, args.warmup, nq, cfg["n"])
         finally:

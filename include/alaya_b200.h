@@ -111,7 +111,10 @@ int ab_index_load(ab_index *index, const char *index_path, const char *data_path
 /* Device-resident entry points (inputs/outputs already in HBM on the index's device).          */
 /* d_out_dist may be NULL. `stream` is a cudaStream_t; the call is asynchronous on it            */
 /* (NULL = the legacy default stream).                                                         */
-/* rerank != 0 applies the SQ re-rank of batch_search; 0 returns the search-space pool order.   */
+/* rerank: bit 0 applies the SQ re-rank of batch_search (0 returns the search-space pool order);  */
+/* bit 1 marks list slots the index could not fill as (0xFFFFFFFF, FLT_MAX) instead of the        */
+/* reference's zero padding and leaves the (ef - topk) zero slots out of the re-rank -- for       */
+/* per-shard lists that are merged afterwards (ab_merge_topk_device skips such entries).          */
 int ab_index_batch_search_device(ab_index *index, const float *d_queries, uint64_t nq, uint32_t topk,
                                  uint32_t ef, int32_t rerank, uint32_t *d_out_ids, float *d_out_dist,
                                  void *stream);

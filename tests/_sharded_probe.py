@@ -1,5 +1,7 @@
-"""Helper for test_gpu_multi.py, launched with torch.distributed.run on 2+ GPUs: every rank builds one shard,
-then the merged results of the peer-memory exchange must equal those of the NCCL exchange and the exact merge."""
+"""Helper for test_gpu_multi.py, launched with torch.distributed.run on 2+ GPUs: every rank builds one shard of one
+logical index; the fused exchange (ab_comm: peer stores over NVLink + last-arriver merge) must equal the collective
+route (NCCL all-gather + merge kernel) and the exact CPU merge of the shards' own lists, for raw and SQ8 spaces, and
+the SQ shards must carry the single index's codes (global quantiser range)."""
 import os
 import sys
 
@@ -9,44 +11,39 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alayalite_b200 import _cabi  # noqa: E402
-from alayalite_b200.sharded import ShardedIndex  # noqa: E402
+from alayalite_b200.sharded import ShardedIndex, global_quantizer_range, shard_range  # noqa: E402
 from alayalite_b200.synthetic import low_rank  # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+_cabi.check(_cabi.lib().ab_set_device(int(os.environ["LOCAL_RANK"])))
 dist.init_process_group("nccl", device_id=dev)
-n, dim, nq, k = 20000, 64, 500, 10
-base, q = low_rank(n, dim, nq, 12, seed=9, shard=rank)
-ix = _cabi.NativeIndex("l2", "none", n)
+n_total, dim, nq, k = 40000, 64, 501, 10
+full, q = low_rank(n_total, dim, nq, 12, seed=9)
+r0, r1 = shard_range(n_total, world, rank)
+base = full[r0:r1]
+ix = _cabi.NativeIndex("l2", "none", len(base), device=int(os.environ["LOCAL_RANK"]))
 ix.fit(base, 80)
 stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
 d_q = torch.from_numpy(q).to(dev)
-peer = ShardedIndex(ix, rank * n, world, peer_memory=True)
-nccl = ShardedIndex(ix, rank * n, world, peer_memory=False)
+fused = ShardedIndex(ix, r0, world, peer_memory=True)
+coll = ShardedIndex(ix, r0, world, peer_memory=False)
 ok = True
 for it in range(4):  # several steps: exercises the two buffer parities
     for ef in (16, 64):
-        a_ids, a_dist = [t.clone() for t in peer.batch_search_device(d_q, k, ef, stream.cuda_stream)]
-        b_ids, b_dist = [t.clone() for t in nccl.batch_search_device(d_q, k, ef, stream.cuda_stream)]
+        a_ids, a_dist = [t.clone() for t in fused.batch_search_device(d_q, k, ef, stream)]
+        b_ids, b_dist = [t.clone() for t in coll.batch_search_device(d_q, k, ef, stream.cuda_stream)]
         torch.cuda.synchronize()
         ok &= bool(torch.equal(a_ids, b_ids) and torch.equal(a_dist, b_dist))
-# host route: pinned buffers are used in place, pageable ones are copied; same answer either way
-qp = torch.from_numpy(q).pin_memory()
-outp = torch.full((nq, k), -1, dtype=torch.int32).pin_memory()
-peer.batch_search(qp, k, 64, out=outp, device=dev, stream=stream.cuda_stream)
-got_np = peer.batch_search(q, k, 64, device=dev, stream=stream.cuda_stream)
-ok &= bool(np.array_equal(outp.numpy(), a_ids.cpu().numpy()) and np.array_equal(got_np.view(np.int32), a_ids.cpu().numpy()))
-# every rank holds the same merged list
-g = [torch.empty_like(a_ids) for _ in range(world)]
-dist.all_gather(g, a_ids)
-ok &= all(bool(torch.equal(g[0], x)) for x in g)
-# and it is what an exact merge of the shards' own lists gives
+        ok &= a_ids.shape[0] == len(fused.owned(nq))
+# the full merged result on every rank, and what an exact merge of the shards' own lists gives
+got = fused.batch_search(q, k, 64, device=dev, stream=stream)
 ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
 dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
 ix.batch_search_device(d_q.data_ptr(), nq, k, 64, ids.data_ptr(), dd.data_ptr(), True, stream.cuda_stream)
-ids += rank * n
+ids += r0
 gi = [torch.empty_like(ids) for _ in range(world)]
 gd = [torch.empty_like(dd) for _ in range(world)]
 dist.all_gather(gi, ids)
@@ -55,19 +52,25 @@ torch.cuda.synchronize()
 ci, cd = torch.cat(gi, 1).cpu().numpy().astype(np.int64), torch.cat(gd, 1).cpu().numpy()
 order = np.lexsort((ci, cd), axis=1)[:, :k]
 want = np.take_along_axis(ci, order, 1)
-ok &= bool(np.array_equal(want, a_ids.cpu().numpy().astype(np.int64)))
-# quantised space: the final lists come from the re-rank kernel, which carries the peer stores there
-ix8 = _cabi.NativeIndex("l2", "sq8", n)
-ix8.fit(base, 80)
-peer8 = ShardedIndex(ix8, rank * n, world, peer_memory=True)
-nccl8 = ShardedIndex(ix8, rank * n, world, peer_memory=False)
+ok &= bool(np.array_equal(want, got.astype(np.int64)))
+ok &= bool(np.array_equal(want[rank::world], a_ids.cpu().numpy().astype(np.int64)))
+# quantised space: global range at fit time, final lists from the re-rank kernel
+mn, mx = global_quantizer_range("l2", base)
+ix8 = _cabi.NativeIndex("l2", "sq8", len(base), device=int(os.environ["LOCAL_RANK"]))
+_cabi.fit_ranged(ix8, base, ef_construction=80, mn=mn, mx=mx)
+wmn, wmx, wcodes = _cabi.quant_fit_encode("sq8", full)  # the single index's quantiser
+smn, smx, scodes = ix8.codes()
+ok &= bool(np.array_equal(smn, wmn) and np.array_equal(smx, wmx) and np.array_equal(scodes, wcodes[r0:r1]))
+fused8 = ShardedIndex(ix8, r0, world, peer_memory=True)
+coll8 = ShardedIndex(ix8, r0, world, peer_memory=False)
 for ef in (32, 100):
-    p_ids, p_dist = [t.clone() for t in peer8.batch_search_device(d_q, k, ef, stream.cuda_stream)]
-    c_ids, c_dist = [t.clone() for t in nccl8.batch_search_device(d_q, k, ef, stream.cuda_stream)]
+    p_ids, p_dist = [t.clone() for t in fused8.batch_search_device(d_q, k, ef, stream)]
+    c_ids, c_dist = [t.clone() for t in coll8.batch_search_device(d_q, k, ef, stream)]
     torch.cuda.synchronize()
     ok &= bool(torch.equal(p_ids, c_ids) and torch.equal(p_dist, c_dist))
-print(f"rank {rank} ok={ok} exchange={peer.exchange_kind!r} err={getattr(peer, 'peer_error', None)}", flush=True)
-flag = torch.tensor([int(ok and peer.exchange_kind.startswith('peer'))], device=dev)
+errs = (fused._comm.errors() if fused._comm else -1, fused8._comm.errors() if fused8._comm else -1)
+print(f"rank {rank} ok={ok} exchange={fused.exchange_kind!r} err={fused.peer_error} comm_errors={errs}", flush=True)
+flag = torch.tensor([int(ok and fused.exchange_kind.startswith('fused') and errs == (0, 0))], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) == 1 else 1)

@@ -1,0 +1,154 @@
+"""Shard exchange fused into the search epilogue (csrc/exchange.cuh, ab_group / ab_comm), on ONE GPU: the shards of a
+group may live on the same device, which exercises the whole protocol -- mailbox stores, system-scope arrival
+counters, last-arriver merge, parities, owner rows -- on the driver's single-GPU test box. tests/test_gpu_multi.py
+repeats it across real NVLink peers.
+
+Oracle: the reference has no sharded mode; the contract is "what a CPU merge by (distance, id) of the
+per-shard results gives", with the per-shard results themselves pinned against the oracle by the parity suites."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _merge_reference(per_shard, offsets, k):
+    """per_shard: list of (ids [nq, k], dist [nq, k], valid [nq] = entries that are real) -> merged ids / dist."""
+    nq = per_shard[0][0].shape[0]
+    out_i = np.zeros((nq, k), np.uint32)
+    out_d = np.zeros((nq, k), np.float32)
+    for q in range(nq):
+        ent = []
+        for (ids, dist, valid), off in zip(per_shard, offsets):
+            for j in range(int(valid[q])):
+                ent.append((float(dist[q, j]), int(ids[q, j]) + off))
+        ent.sort()
+        for r, (d, i) in enumerate(ent[:k]):
+            out_i[q, r], out_d[q, r] = i, d
+    return out_i, out_d
+
+
+def _shard_lists(ix, q, k, ef):
+    """One shard's own final lists + how many entries of each are real (pool size, capped at k)."""
+    ids, dist = ix.batch_search_with_distance(q, k, ef)
+    _, _, sizes = ix.traverse(q, ef)
+    return ids, dist, np.minimum(sizes, k)
+
+
+@pytest.mark.parametrize("shards,k,ef", [(2, 10, 48), (3, 10, 100), (4, 100, 128), (8, 10, 32)])
+def test_group_raw_equals_cpu_merge_of_shard_lists(cabi, small_sets, shards, k, ef):
+    base, q = small_sets["lowrank"]
+    g = cabi.Group("l2", "none", len(base), devices=[0] * shards, n_shards=shards)
+    g.fit(base, 60)
+    per = (len(base) + shards - 1) // shards
+    lists = [_shard_lists(g.shard(s), q, k, ef) for s in range(shards)]
+    want_i, want_d = _merge_reference(lists, [s * per for s in range(shards)], k)
+    for _ in range(3):  # consecutive calls alternate the buffer parities
+        got_i, got_d = g.batch_search(q, k, ef, with_distance=True)
+        assert np.array_equal(got_i, want_i)
+        assert np.array_equal(got_d, want_d)
+    # the merged list is at least as good as any single shard's and close to exact
+    gt, _ = cabi.bruteforce_topk("l2", base, q, k)
+    rec = np.mean([len(set(got_i[i]) & set(gt[i])) / k for i in range(len(q))])
+    assert rec > 0.9
+
+
+def test_group_tiny_shards_pad_instead_of_row_zero(cabi):
+    """Shards smaller than topk cannot fill their lists: the padding must not enter the merge as 'row 0 at distance 0'."""
+    from alayalite_b200.synthetic import low_rank
+    base, q = low_rank(36, 16, 20, latent=4, seed=11)
+    g = cabi.Group("l2", "none", 36, devices=[0, 0, 0], n_shards=3)
+    g.fit(base, 40)
+    ids, dist = g.batch_search(q, 20, 32, with_distance=True)
+    gt, gd = cabi.bruteforce_topk("l2", base, q, 20)
+    assert np.array_equal(ids, gt)  # 12-row shards are searched exhaustively at ef 32
+    np.testing.assert_allclose(dist, gd, rtol=1e-5)
+    for row in ids:
+        assert len(set(row.tolist())) == 20
+
+
+@pytest.mark.parametrize("quant,metric", [("sq8", "l2"), ("sq4", "ip")])
+def test_group_sq_uses_global_range_and_merges_reranked_lists(cabi, small_sets, quant, metric):
+    base, q = small_sets["lowrank128"]
+    shards, k, ef = 3, 10, 64
+    g = cabi.Group(metric, quant, len(base), devices=[0] * shards, n_shards=shards)
+    g.fit(base, 60)
+    single = cabi.NativeIndex(metric, quant, len(base))
+    single.fit(base, 60)
+    mn, mx, codes = single.codes()
+    per = (len(base) + shards - 1) // shards
+    for s in range(shards):  # sharded codes must equal the single index's codes
+        smn, smx, scodes = g.shard(s).codes()
+        assert np.array_equal(smn, mn) and np.array_equal(smx, mx)
+        assert np.array_equal(scodes, codes[s * per:(s + 1) * per])
+    got_i, got_d = g.batch_search(q, k, ef, with_distance=True)
+    # per-shard re-ranked lists (bit 1 of the flag: no zero-fill slots, unfilled = 0xFFFFFFFF) merged on the CPU
+    import torch
+    dq = torch.from_numpy(q).cuda()
+    lists = []
+    for s in range(shards):
+        ids = torch.empty((len(q), k), dtype=torch.int32, device="cuda")
+        dd = torch.empty((len(q), k), dtype=torch.float32, device="cuda")
+        g.shard(s).batch_search_device(dq.data_ptr(), len(q), k, ef, ids.data_ptr(), dd.data_ptr(), 3, None)
+        torch.cuda.synchronize()
+        i_np = ids.cpu().numpy().view(np.uint32)
+        lists.append((i_np, dd.cpu().numpy(), (i_np != 0xFFFFFFFF).sum(1)))
+    want_i, want_d = _merge_reference(lists, [s * per for s in range(shards)], k)
+    assert np.array_equal(got_i, want_i)
+    assert np.array_equal(got_d, want_d)
+
+
+def test_group_replicas_split_the_batch(cabi, small_sets):
+    base, q = small_sets["lowrank"]
+    single = cabi.NativeIndex("l2", "none", len(base))
+    single.fit(base, 60)
+    g = cabi.Group("l2", "none", len(base), devices=[0, 0, 0], n_shards=1, n_replicas=3)
+    g.fit(base, 60)
+    # every replica builds its own graph; on one GPU model the build is deterministic enough that recall is what we pin
+    gt, _ = cabi.bruteforce_topk("l2", base, q, 10)
+    got = g.batch_search(q, 10, 64)
+    rec = np.mean([len(set(got[i]) & set(gt[i])) / 10 for i in range(len(q))])
+    assert rec > 0.95
+    # 2 shards x 2 replicas: each replica group merges its own half of the batch
+    g2 = cabi.Group("l2", "none", len(base), devices=[0] * 4, n_shards=2, n_replicas=2)
+    g2.fit(base, 60)
+    got2 = g2.batch_search(q[:101], 10, 64)  # odd batch: uneven split, uneven ownership
+    rec2 = np.mean([len(set(got2[i]) & set(gt[i])) / 10 for i in range(101)])
+    assert rec2 > 0.95
+
+
+def test_comm_owner_rows_one_process_two_ranks(cabi, small_sets):
+    """The per-rank API (what torchrun ranks call) with both ranks in this process: handles exchanged by hand, one stream
+    per rank, every rank receives the merged rows it owns."""
+    import torch
+    base, q = small_sets["lowrank"]
+    world, k, ef = 2, 10, 64
+    per = (len(base) + world - 1) // world
+    shards, comms = [], []
+    for r in range(world):
+        ix = cabi.NativeIndex("l2", "none", per)
+        ix.fit(base[r * per:(r + 1) * per], 60)
+        shards.append(ix)
+        comms.append(cabi.Comm(ix, r, world, r * per, 1000, 16))
+    for c in comms:
+        c.connect([x.handle for x in comms])
+    lists = [_shard_lists(ix, q, k, ef) for ix in shards]
+    want_i, want_d = _merge_reference(lists, [0, per], k)
+    dq = torch.from_numpy(q).cuda()
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for it in range(4):
+        outs = []
+        for r, c in enumerate(comms):
+            n_own = c.owned(len(q))
+            ids = torch.full((n_own, k), -1, dtype=torch.int32, device="cuda")
+            dd = torch.zeros((n_own, k), dtype=torch.float32, device="cuda")
+            c.batch_search_device(dq.data_ptr(), len(q), k, ef, ids.data_ptr(), dd.data_ptr(), streams[r].cuda_stream)
+            outs.append((ids, dd))
+        torch.cuda.synchronize()
+        for r, (ids, dd) in enumerate(outs):
+            assert np.array_equal(ids.cpu().numpy().view(np.uint32), want_i[r::world]), (it, r)
+            assert np.array_equal(dd.cpu().numpy(), want_d[r::world]), (it, r)
+    assert all(c.errors() == 0 for c in comms)
+    for c in comms:
+        c.close()
