@@ -345,6 +345,43 @@ __device__ __forceinline__ float raw_distance_multi(const uint8_t *r0, const uin
   return reduce_multi<IP, TPV, NC>(f2sum(a0), f2sum(a1), f2sum(a2), lg);
 }
 
+// Six (five, four) candidates per group in flight: the deep variant for launches that shared memory limits to a
+// dozen resident warps (large ef). The registers that twice the warps would have used hold twice the rows instead,
+// so a hop of up to 24 new neighbours is evaluated in ONE pass over memory instead of two. Candidates 0..2 come back
+// like raw_distance_multi<3> (lanes with lg % 4 == c), candidates 3..5 in `d_hi` the same way.
+template <bool IP, int TPV, int CPL, bool EXACT, int NC>
+__device__ __forceinline__ float raw_distance_deep(const uint8_t *const (&r)[6], const float *q_smem, int nchunks, int lg, float &d_hi) {
+  static_assert(NC >= 4 && NC <= 6 && TPV >= 4, "");
+  U64x2 x[NC][CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (EXACT || lg + i * TPV < nchunks) {
+        x[c][i] = ldg128_pairs(r[c] + i * TPV * 16);
+      } else {
+        x[c][i].a = x[c][i].b = 0ull;
+      }
+    }
+  }
+  __syncwarp();  // scheduling fence: every load is issued before the first shared-memory read / FMA
+  unsigned long long a[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+  for (int i = 0; i < CPL; i++) {
+    U64x2 q;
+    q.a = q.b = 0ull;
+    if (EXACT || lg + i * TPV < nchunks) {
+      const ulonglong2 t = reinterpret_cast<const ulonglong2 *>(q_smem)[lg + i * TPV];
+      q.a = t.x;
+      q.b = t.y;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) a[c] = raw_pairs_term<IP>(q, x[c][i], a[c]);
+  }
+  d_hi = reduce_multi<IP, TPV, NC - 3>(f2sum(a[3]), f2sum(a[4]), f2sum(a[5]), lg);
+  return reduce_multi<IP, TPV, 3>(f2sum(a[0]), f2sum(a[1]), f2sum(a[2]), lg);
+}
+
 // ---- SQ8 / SQ4, three candidates per group in flight ----------------------------------------------
 // Same shape as raw_distance_multi. A lane owns chunk index lg + i * TPV of all three candidates, so the
 // query codes and the per-dimension tables of a chunk are expanded once and used three times, and the

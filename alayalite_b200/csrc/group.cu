@@ -49,19 +49,30 @@ struct HandleBlob {
 };
 static_assert(sizeof(HandleBlob) <= AB_COMM_HANDLE_BYTES, "handle blob too large");
 
-__global__ void wait_done_kernel(unsigned long long *done, unsigned long long expect, uint32_t *err) {
-  // one thread: poll the counter the merging warps of every shard bump (system-scope atomics into this memory)
-  const long long t0 = clock64();
-  volatile unsigned long long *d = done;
-  while (*d < expect) {
-    __nanosleep(200);
-    if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer never delivered; report instead of hanging the device
-      atomicAdd(err, 1u);
-      break;
+// One block behind the search on the rank's stream: thread 0 polls the counter the merging warps of every shard bump
+// (system-scope atomics into this rank's memory), then all threads copy the owned merged rows to the caller's buffers
+// (device or pinned host memory) -- one launch instead of a wait kernel and two copies.
+__global__ void __launch_bounds__(1024) wait_copy_kernel(unsigned long long *done, unsigned long long expect, uint32_t *err,
+                                                         const uint32_t *src_ids, const float *src_dist, uint32_t *dst_ids,
+                                                         float *dst_dist, size_t words) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    volatile unsigned long long *d = done;
+    while (*d < expect) {
+      __nanosleep(100);
+      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer never delivered; report instead of hanging the device
+        atomicAdd(err, 1u);
+        break;
+      }
     }
+    *d = 0ull;  // this parity is not touched again before every shard has finished the next call
+    __threadfence_system();
   }
-  *d = 0ull;  // this parity is not touched again before every shard has finished the next call
-  __threadfence_system();
+  __syncthreads();
+  for (size_t i = threadIdx.x; i < words; i += blockDim.x) {
+    dst_ids[i] = __ldcg(src_ids + i);  // rows arrive from other GPUs: read at L2
+    if (dst_dist) dst_dist[i] = __ldcg(src_dist + i);
+  }
 }
 
 }  // namespace
@@ -306,13 +317,11 @@ int ab_comm_batch_search_device(ab_comm *comm, const float *d_queries, uint64_t 
     // rows this rank owns: queries rank, rank + world, ...
     const uint64_t owned = nq > comm->rank ? (nq - comm->rank + comm->world - 1) / comm->world : 0;
     uint8_t *b = comm->region + pb;
-    wait_done_kernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned long long *>(b + comm->off_done), owned, comm->err.p);
+    wait_copy_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<unsigned long long *>(b + comm->off_done), owned, comm->err.p,
+                                        reinterpret_cast<const uint32_t *>(b + comm->off_ids), reinterpret_cast<const float *>(b + comm->off_dist),
+                                        d_out_ids, d_out_dist, size_t(owned) * topk);
     AB_CUDA(cudaGetLastError());
     count_launch();
-    if (owned > 0) {
-      AB_CUDA(cudaMemcpyAsync(d_out_ids, b + comm->off_ids, owned * topk * 4, cudaMemcpyDefault, s));
-      if (d_out_dist) AB_CUDA(cudaMemcpyAsync(d_out_dist, b + comm->off_dist, owned * topk * 4, cudaMemcpyDefault, s));
-    }
   });
 }
 

@@ -131,6 +131,8 @@ bool launch_raw_fast(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
   if (n == T * C) { launch_one<AB_QUANT_NONE, IP, T, C, true>(p, a, s); return true; }
 #define AB_FAST_LE(T, C)                                                \
   if (n <= T * C) { launch_one<AB_QUANT_NONE, IP, T, C, false>(p, a, s); return true; }
+  if (p.deep && n == 24) { launch_one<AB_QUANT_NONE, IP, 8, 3, true, 6>(p, a, s); return true; }
+  if (p.deep && n == 32) { launch_one<AB_QUANT_NONE, IP, 8, 4, true, 6>(p, a, s); return true; }
   AB_FAST(8, 3)    // d = 96
   AB_FAST(8, 4)    // d = 128
   AB_FAST(16, 4)   // d = 256
@@ -188,8 +190,32 @@ void VisitedWorkspace::fill(SearchArgs &a) const {
 
 float visited_model(uint32_t ef) { return 16.0f + 400.0f / static_cast<float>(std::max(1u, ef)); }
 
+static SearchPlan plan_search_impl(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
+                                   int sm_count, size_t smem_limit, size_t min_warp_bytes, int reg_cap, int wpc_cap);
+
 SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
                        int sm_count, size_t smem_limit, size_t min_warp_bytes) {
+  SearchPlan p = plan_search_impl(quant, nchunks, table_len, visit_ratio, ef, nq, n_rows, sm_count, smem_limit, min_warp_bytes, 64, 8);
+  // Deep variant (six candidate rows per lane group in flight instead of three): when shared memory -- the visited
+  // table of a large ef -- leaves room for no more warps than the deep kernel's registers allow anyway, the same
+  // warps carry twice the rows in flight. d = 96: 16 warps (128 registers), d = 128: 12 warps of 6 per CTA (168).
+  static const int deep_on = getenv("AB_DEEP") ? atoi(getenv("AB_DEEP")) : 1;
+  if (deep_on && quant == AB_QUANT_NONE && (nchunks == 24 || nchunks == 32)) {
+    const int cap = nchunks == 24 ? 16 : 12, wpc = nchunks == 24 ? 8 : 6;
+    const int have = p.warps_per_cta * p.ctas_per_sm;
+    if (deep_on == 2 || have <= cap) {
+      SearchPlan d = plan_search_impl(quant, nchunks, table_len, visit_ratio, ef, nq, n_rows, sm_count, smem_limit, min_warp_bytes, cap, wpc);
+      if (deep_on == 2 || 2 * d.warps_per_cta * d.ctas_per_sm > have + have / 4) {
+        d.deep = 1;
+        return d;
+      }
+    }
+  }
+  return p;
+}
+
+static SearchPlan plan_search_impl(int quant, int nchunks, int table_len, float visit_ratio, uint32_t ef, uint32_t nq, uint32_t n_rows,
+                                   int sm_count, size_t smem_limit, size_t min_warp_bytes, int reg_cap, int wpc_cap) {
   SearchPlan p{};
   p.tpv = pick_tpv(nchunks);
   static const float hash_factor = getenv("AB_HASH_FACTOR") ? static_cast<float>(atof(getenv("AB_HASH_FACTOR"))) : 1.7f;
@@ -235,7 +261,7 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   }
   // resident warps the register file allows: the three-in-flight raw kernels are built for 3 x 256 threads,
   // everything else (SQ spaces, rows above 128 chunks) for 2 x 256
-  const int reg_warps = std::min(max_warps, (quant == AB_QUANT_NONE && nchunks <= 128) ? 8 * AB_MINBLOCKS : 16);
+  const int reg_warps = std::min(std::min(max_warps, reg_cap), (quant == AB_QUANT_NONE && nchunks <= 128) ? 8 * AB_MINBLOCKS : 16);
   // Full register-limited occupancy under a 196 KB carve-out is worth a tighter table (the step from 24 to
   // 20 warps costs ~25 % at ef 100): shrink down to 1.3 / 1.7 of the wanted size for it. Below 12 resident
   // warps, shrink further and let long queries continue in their global bitmap.
@@ -269,7 +295,7 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   auto pack = [&](size_t limit, int &wpc_out, int &ctas_out) {
     wpc_out = 1;
     ctas_out = 0;
-    for (int wpc = 8; wpc >= 1; --wpc) {
+    for (int wpc = wpc_cap; wpc >= 1; --wpc) {
       const int by_smem = static_cast<int>(limit / (cta_fixed + size_t(wpc) * pw + 1024));
       const int ctas = std::min(by_smem, reg_warps / wpc);
       if (ctas * wpc > ctas_out * wpc_out) {

@@ -99,6 +99,7 @@ struct SearchPlan {
   size_t smem_bytes;
   int slots;          // ctas * warps_per_cta (overflow-table slots needed)
   int max_slots;      // slots any plan for this batch size could need (workspace sizing)
+  int deep;           // 1: the six-in-flight kernel variant (raw rows of 24 / 32 chunks, at most 16 / 12 resident warps)
   uint32_t ovf_size;  // entries of one overflow table (power of two)
 };
 

@@ -152,8 +152,8 @@ __device__ __noinline__ void visit_overflow_release(const SearchArgs &a, Visited
 //  * 16-bit entries (a.hash_rbits > 0) when the id range is small enough relative to the table: the id is
 //    scrambled by a bijection of the b-bit id space (odd multiplier mod 2^b), the table slot is the scaled
 //    scramble, and the entry keeps what the slot does not already say -- the position inside the slot's
-//    bucket of the id space (r, rbits bits) and the displacement from the home slot (linear probing). An
-//    entry equal to (displacement, r) at slot home + displacement can only belong to this id. Half the
+//    bucket of the id space (r, rbits bits) and the displacement from the home slot in probe steps. An
+//    entry equal to (displacement, r) at slot home + displacement * step(r) can only belong to this id. Half the
 //    shared memory per warp, which matters twice: more resident warps, and more of the unified L1/shared
 //    array left to stage loads in flight. A probe that runs out of displacement range falls through to
 //    the warp's overflow table (exact).
@@ -167,6 +167,11 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
     uint32_t slot = __umulhi(x, hsize);
     uint32_t code = __umulhi(x * hsize, a.hash_rmul);  // displacement 0
     const uint32_t dstep = 1u << a.hash_rbits;
+    // Probe sequence home, home + t, home + 2t, ... with an odd step t in 1..31 taken from the remainder: no primary
+    // clustering (unsuccessful probes at 3/4 load: ~4 instead of ~8.5, and the warp iterates as long as its slowest
+    // lane). Exactness is untouched: an entry (displacement d, remainder r) at slot s can only belong to the id with
+    // home s - d * t(r) and remainder r.
+    const uint32_t stride = 1u + 2u * (code & 15u);
     // Probe with plain reads; only an empty slot is claimed, with a 32-bit CAS on the word that holds it
     // (a failed CAS -- the slot or its neighbour half changed meanwhile -- re-reads the same slot).
     while (__any_sync(kFull, pending)) {
@@ -190,7 +195,8 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
           pending = false;
         }
         if (pending && advance) {
-          slot = slot + 1 == hsize ? 0u : slot + 1;
+          slot += stride;  // double hashing: the step is a function of the remainder, which the entry stores
+          slot = slot >= hsize ? slot - hsize : slot;
           code += dstep;
           if (code >= a.hash_dlimit) {  // out of displacement range
             pending = false;
@@ -472,7 +478,7 @@ __device__ __forceinline__ float multi_distance(const uint8_t *r0, const uint8_t
 #ifndef AB_MINBLOCKS
 #define AB_MINBLOCKS 3
 #endif
-template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT, int INFL>
 __device__ __forceinline__ float eval_lanes_multi(const SearchArgs &a, const WarpSmem &ws, const QuerySmem &qs, uint32_t v,
                                                   bool want, int lane) {
   constexpr int G = 32 / TPV;
@@ -483,11 +489,35 @@ __device__ __forceinline__ float eval_lanes_multi(const SearchArgs &a, const War
   __syncwarp();
   const int g = lane / TPV, lg = lane % TPV;
   const uint8_t *lane_base = a.rows + lg * 16;
-  for (int base = 0; base < cnt; base += AB_INFLIGHT * G) {
+  for (int base = 0; base < cnt; base += INFL * G) {
     const int rem = cnt - base;  // warp-uniform
     const int k0 = base + g, k1 = k0 + G, k2 = k1 + G;
     const uint8_t *r0 = lane_base + size_t(ws.cand[k0 < cnt ? k0 : 0]) * a.row_stride;
-    if (AB_INFLIGHT > 2 && rem > 2 * G) {
+    if constexpr (INFL == 6 && QUANT == AB_QUANT_NONE) {
+      if (rem > 3 * G) {  // deep pass: four to six candidates per group
+        const uint8_t *r[6];
+        r[0] = r0;
+#pragma unroll
+        for (int c = 1; c < 6; c++) {
+          const int kc = k0 + c * G;
+          r[c] = lane_base + size_t(ws.cand[kc < cnt ? kc : 0]) * a.row_stride;
+        }
+        float d_hi, d_lo;
+        if (rem > 5 * G) {
+          d_lo = raw_distance_deep<IP, TPV, CPL, EXACT, 6>(r, qs.q_raw, a.nchunks, lg, d_hi);
+        } else if (rem > 4 * G) {
+          d_lo = raw_distance_deep<IP, TPV, CPL, EXACT, 5>(r, qs.q_raw, a.nchunks, lg, d_hi);
+        } else {
+          d_lo = raw_distance_deep<IP, TPV, CPL, EXACT, 4>(r, qs.q_raw, a.nchunks, lg, d_hi);
+        }
+        // lanes 0..2 of the group hold candidates 0..2 (d_lo) and 3..5 (d_hi)
+        const int klo = k0 + lg * G, khi = klo + 3 * G;
+        if (lg < 3 && klo < cnt) ws.cdist[klo] = d_lo;
+        if (lg < 3 && khi < cnt) ws.cdist[khi] = d_hi;
+        continue;
+      }
+    }
+    if (INFL > 2 && rem > 2 * G) {
       const uint8_t *r1 = lane_base + size_t(ws.cand[k1 < cnt ? k1 : 0]) * a.row_stride;
       const uint8_t *r2 = lane_base + size_t(ws.cand[k2 < cnt ? k2 : 0]) * a.row_stride;
       const float d = multi_distance<QUANT, IP, TPV, CPL, EXACT, 3>(r0, r1, r2, qs, a.nchunks, lg);
@@ -511,8 +541,11 @@ __device__ __forceinline__ float eval_lanes_multi(const SearchArgs &a, const War
 
 // CPL > 0 selects the raw-space fast path (needs QUANT == none and TPV * CPL >= nchunks; EXACT: ==);
 // CPL == 0 is the generic path for any space.
-template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
-__global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? AB_MINBLOCKS : 2) beam_search_kernel(const SearchArgs a) {
+// INFL: candidates per lane group in flight (3, or 6 = the deep variant: 12 / 16 resident warps by registers)
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT, int INFL = AB_INFLIGHT>
+__global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
+                                  INFL == 6 ? 2 : ((QUANT == AB_QUANT_NONE && CPL > 0 && CPL <= 4) ? AB_MINBLOCKS : 2))
+    beam_search_kernel(const SearchArgs a) {
   constexpr bool FAST = QUANT == AB_QUANT_NONE && CPL > 0;
   constexpr int MAXC = 8;
   // three candidates in flight, query from shared memory (raw rows, and SQ codes with packed arithmetic)
@@ -636,7 +669,7 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
     auto eval = [&](uint32_t id, bool want) -> float {
       float dd;
       if constexpr (FAST3) {
-        dd = eval_lanes_multi<QUANT, IP, TPV, CPL, EXACT>(a, ws, qs, id, want, lane);
+        dd = eval_lanes_multi<QUANT, IP, TPV, CPL, EXACT, INFL>(a, ws, qs, id, want, lane);
       } else if constexpr (FAST) {
         dd = eval_lanes_raw<IP, TPV, QREGS, EXACT>(a, ws, qreg, id, want, lane);
       } else {
@@ -811,9 +844,9 @@ __global__ void __launch_bounds__(256, (QUANT == AB_QUANT_NONE && CPL > 0 && CPL
 
 #undef AB_EVAL
 
-template <int QUANT, bool IP, int TPV, int CPL, bool EXACT>
+template <int QUANT, bool IP, int TPV, int CPL, bool EXACT, int INFL = AB_INFLIGHT>
 void launch_one(const SearchPlan &p, const SearchArgs &a, cudaStream_t s) {
-  auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT>;
+  auto kern = beam_search_kernel<QUANT, IP, TPV, CPL, EXACT, INFL>;
   AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem_bytes)));
   // The unified L1 / shared-memory array also stages the row loads in flight: ask for exactly the shared memory
   // the resident CTAs need and leave the rest to L1.

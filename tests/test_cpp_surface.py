@@ -50,3 +50,18 @@ def test_cpp_surface_end_to_end(tmp_path):
     assert head == "same=1 solo_same=1 sorted=1 dist_ok=1 n=4000", head
     ids = np.array(ids.split(), dtype=np.uint32).reshape(50, 10)
     assert len(np.unique(ids[0])) == 10 and ids.max() < 4000
+
+
+@pytest.mark.gpu
+def test_plain_c_host_runs_a_two_shard_search(tmp_path):
+    """ab_group_* from a C program: no torch, no NCCL, no C++."""
+    exe = str(tmp_path / "shard")
+    lib_dir = os.path.join(ROOT, "alayalite_b200")
+    cmd = ["gcc", "-O2", "-std=c11", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "shard_gpu.c"), "-o", exe,
+           "-L", lib_dir, "-lalaya_b200", "-Wl,-rpath," + lib_dir]
+    c = subprocess.run(cmd, capture_output=True, text=True)
+    assert c.returncode == 0, c.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    fields = dict(f.split("=") for f in r.stdout.split())
+    assert float(fields["recall"]) >= 0.97 and fields["sorted"] == "1" and int(fields["ids_from_second_shard"]) > 0

@@ -210,11 +210,40 @@ def test_search_sq_matches_oracle(cabi, orc, small_sets, metric, quant):
         assert np.array_equal(mn, omn) and np.array_equal(mx, omx)
         assert np.array_equal(codes, o.codes())
     agree = []
+    rows = o.raw_rows()
+    ocodes = o.codes()
+    bits = 8 if quant == "sq8" else 4
+    kern = ("l2" if metric == "l2" else "ip") + "_sqr_" + quant
+
+    def qcode(i):  # the query encoded like SQ8Space::QueryComputer does (un-normalised, sq8_space.hpp:264-269)
+        c = [orc.quantize(bits, float(q[i][d]), float(omn[d]), float(omx[d])) for d in range(q.shape[1])]
+        if bits == 8:
+            return np.array(c, np.uint8)
+        c += [0] * (len(c) % 2)
+        return np.array([(c[2 * j] << 4) | c[2 * j + 1] for j in range(len(c) // 2)], np.uint8)
+
     for ef, k in ((10, 10), (64, 10), (100, 100), (120, 7)):
         want = o.batch_search(q, k, ef)
         got = ix.batch_search(q, k, ef)
-        agree.append(np.mean(np.all(got == want, axis=1)))
+        same = np.all(got == want, axis=1)
+        agree.append(same.mean())
         assert recall(got, want) >= 0.98, (metric, quant, ef, k)
+        # Every differing row must be explained by a tie: the same raw distances (a re-ordering inside the re-rank),
+        # or a code-space tie at the top-k cut of the pool, which swaps one id for another of equal code distance.
+        g_pool, g_pd, g_sz = ix.traverse(q, ef)
+        for i in np.nonzero(~same)[0]:
+            qq = orc.normalize(q[i]) if metric == "cos" else q[i]
+            f = lambda ids: np.sort([orc.dist("l2_sqr" if metric == "l2" else "ip_sqr", qq, rows[int(v)]) for v in ids])  # noqa: E731
+            if _close(f(got[i]), f(want[i]), rel=REL, abs_=1e-5):
+                continue
+            w_pool, w_pd, _ = o.traverse(q[i], ef)
+            m = int(g_sz[i])
+            assert m == len(w_pool) and _close(g_pd[i, :m], w_pd, rel=REL, abs_=1e-6), (metric, quant, ef, k, i)
+            qc = qcode(i)
+            for v in set(g_pool[i, :min(k, m)].tolist()) ^ set(w_pool[:min(k, m)].tolist()):
+                dv = orc.dist(kern, qc, ocodes[int(v)], omn, omx)
+                cut = w_pd[min(k, m) - 1]
+                assert abs(dv - cut) <= REL * max(1.0, abs(cut)), (metric, quant, ef, k, i, v, dv, cut)
     assert min(agree) >= 0.9, agree
     # un-reranked ids + empty distances (index.hpp:395-418)
     ids, dist = ix.batch_search_with_distance(q, 10, 64)
