@@ -187,8 +187,15 @@ void bruteforce_topk(int metric, const float *d_rows, uint64_t n, uint32_t strid
   const uint32_t max_splits = static_cast<uint32_t>(std::max<uint64_t>(1, (n + TB * 8 - 1) / (TB * 8)));
   splits = std::min(splits, max_splits);
   const size_t smem = sizeof(float) * KC * (TQ + 4 + TB + 4) + TQ * 12 + size_t(TQ) * TB * 8 + size_t(TQ) * k * 8;
-  DevBuf<float> pd;
-  DevBuf<uint32_t> pi;
+  // Grow-only partial buffers kept per device: cudaMalloc / cudaFree around every call cost more than the kernel on
+  // small inputs, and freeing forced a stream synchronisation in the middle of the tcgen05 pipeline that calls this
+  // for its innermost sample. Callers are serialised by bruteforce_mutex().
+  static DevBuf<float> pd_all[16];
+  static DevBuf<uint32_t> pi_all[16];
+  int dev = 0;
+  AB_CUDA(cudaGetDevice(&dev));
+  DevBuf<float> &pd = pd_all[dev & 15];
+  DevBuf<uint32_t> &pi = pi_all[dev & 15];
   pd.reserve(size_t(splits) * nq * k);
   pi.reserve(size_t(splits) * nq * k);
   const dim3 grid(qtiles, splits);
@@ -202,7 +209,11 @@ void bruteforce_topk(int metric, const float *d_rows, uint64_t n, uint32_t strid
   AB_CUDA(cudaGetLastError());
   count_launch();
   merge_topk(pd.p, pi.p, splits, nq, k, d_out_ids, d_out_dist, sm_count, s);
-  AB_CUDA(cudaStreamSynchronize(s));  // partial buffers are freed on return
+}
+
+std::mutex &bruteforce_mutex() {
+  static std::mutex mu;
+  return mu;
 }
 
 }  // namespace ab

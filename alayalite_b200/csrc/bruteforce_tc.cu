@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(128) refine_kernel(const float *__restrict__ r
                                                      const uint32_t *__restrict__ cand, const uint32_t *__restrict__ counts,
                                                      uint32_t splits, uint32_t cap, uint32_t k, uint32_t need,
                                                      uint32_t *__restrict__ out_ids, float *__restrict__ out_dist,
-                                                     uint32_t *__restrict__ redo_flags) {
+                                                     uint32_t *__restrict__ redo_flags, uint32_t *__restrict__ redo_count,
+                                                     int threshold_only) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const size_t per_warp = round_up16(size_t(nchunks) * 16 + size_t(k) * 8 + 64 * 4);
@@ -431,11 +432,20 @@ __global__ void __launch_bounds__(128) refine_kernel(const float *__restrict__ r
           topk_insert(td, ti, size, static_cast<int>(k), __shfl_sync(0xFFFFFFFFu, d, j), __shfl_sync(0xFFFFFFFFu, id, j), lane);
       }
     }
+    // threshold_only (the sample level, whose lists only feed the thresholds of the level above): any k real rows
+    // bound the true k-th distance from above, so an overflowed list is still usable as it is; a list with fewer
+    // than k rows is marked empty (threshold = +inf, the level above keeps everything for that query and repairs it)
+    const uint32_t pad_id = threshold_only ? kEmptyId : 0u;
+    const float pad_d = threshold_only ? FLT_MAX : 0.f;
     for (uint32_t i = lane; i < k; i += 32) {
-      out_ids[q * k + i] = i < static_cast<uint32_t>(size) ? ti[i] : 0u;
-      if (out_dist) out_dist[q * k + i] = i < static_cast<uint32_t>(size) ? td[i] : 0.f;
+      out_ids[q * k + i] = i < static_cast<uint32_t>(size) ? ti[i] : pad_id;
+      if (out_dist) out_dist[q * k + i] = i < static_cast<uint32_t>(size) ? td[i] : pad_d;
     }
-    if (lane == 0) redo_flags[q] = (overflow || size < static_cast<int>(need)) ? 1u : 0u;
+    if (lane == 0 && !threshold_only) {
+      const bool again = overflow || size < static_cast<int>(need);
+      redo_flags[q] = again ? 1u : 0u;
+      if (again) atomicAdd(redo_count, 1u);
+    }
     __syncwarp();
   }
 }
@@ -587,7 +597,8 @@ static void tc_run(int metric, const float *d_rows, uint64_t n, uint32_t dim, ui
   count_launch();
 
   // ---- pass C: exact re-evaluation ----------------------------------------------------------------
-  redo.reserve(nq);
+  redo.reserve(nq + 1);
+  AB_CUDA(cudaMemsetAsync(redo.p + nq, 0, 4, s));
   const uint32_t need = static_cast<uint32_t>(std::min<uint64_t>(k, n));
   const int nchunks = static_cast<int>(stride / 4);
   const int warps = 4;
@@ -596,45 +607,48 @@ static void tc_run(int metric, const float *d_rows, uint64_t n, uint32_t dim, ui
   if (l2) {
     AB_CUDA(cudaFuncSetAttribute(refine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     refine_kernel<false><<<blocks, warps * 32, smem, s>>>(d_rows, stride, nchunks, d_queries, qstride, nq, cand.p, counts.p, splits, cap, k,
-                                                       need, d_out_ids, d_out_dist, redo.p);
+                                                       need, d_out_ids, d_out_dist, redo.p, redo.p + nq, level);
   } else {
     AB_CUDA(cudaFuncSetAttribute(refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     refine_kernel<true><<<blocks, warps * 32, smem, s>>>(d_rows, stride, nchunks, d_queries, qstride, nq, cand.p, counts.p, splits, cap, k,
-                                                      need, d_out_ids, d_out_dist, redo.p);
+                                                      need, d_out_ids, d_out_dist, redo.p, redo.p + nq, level);
   }
   AB_CUDA(cudaGetLastError());
   count_launch();
 
   // ---- queries whose survivor list overflowed: exact kernel ---------------------------------------------
+  // The sample level needs no repair (see refine_kernel) and therefore no host round trip. The top level reads back
+  // ONE counter -- the synchronisation the caller needs anyway -- and only a non-zero count costs a second one.
+  if (level != 0) return;
+  uint32_t n_redo = 0;
+  AB_CUDA(cudaMemcpyAsync(&n_redo, redo.p + nq, 4, cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+  if (n_redo == 0) return;
   std::vector<uint32_t> flags(nq);
   AB_CUDA(cudaMemcpyAsync(flags.data(), redo.p, nq * 4, cudaMemcpyDeviceToHost, s));
   AB_CUDA(cudaStreamSynchronize(s));
   std::vector<uint32_t> which;
   for (uint64_t q = 0; q < nq; q++)
     if (flags[q]) which.push_back(static_cast<uint32_t>(q));
-  if (!which.empty()) {
-    const uint32_t m = static_cast<uint32_t>(which.size());
-    DevBuf<uint32_t> dw;
-    DevBuf<float> gq;
-    dw.reserve(m);
-    gq.reserve(size_t(m) * qstride);
-    ri.reserve(size_t(m) * k);
-    rd.reserve(size_t(m) * k);
-    AB_CUDA(cudaMemcpyAsync(dw.p, which.data(), m * 4, cudaMemcpyHostToDevice, s));
-    gather_rows_f32<<<std::min<uint64_t>((uint64_t(m) * qstride + 255) / 256, 4096), 256, 0, s>>>(d_queries, qstride, dw.p, m, gq.p);
-    bruteforce_topk(metric, d_rows, n, stride, gq.p, m, qstride, k, ri.p, rd.p, sm_count, s);
-    scatter_results<<<static_cast<unsigned>((uint64_t(m) * k + 255) / 256), 256, 0, s>>>(ri.p, rd.p, dw.p, m, k, d_out_ids, d_out_dist);
-    AB_CUDA(cudaGetLastError());
-    count_launch(2);
-  }
+  const uint32_t m = static_cast<uint32_t>(which.size());
+  DevBuf<uint32_t> dw;
+  DevBuf<float> gq;
+  dw.reserve(m);
+  gq.reserve(size_t(m) * qstride);
+  ri.reserve(size_t(m) * k);
+  rd.reserve(size_t(m) * k);
+  AB_CUDA(cudaMemcpyAsync(dw.p, which.data(), m * 4, cudaMemcpyHostToDevice, s));
+  gather_rows_f32<<<std::min<uint64_t>((uint64_t(m) * qstride + 255) / 256, 4096), 256, 0, s>>>(d_queries, qstride, dw.p, m, gq.p);
+  bruteforce_topk(metric, d_rows, n, stride, gq.p, m, qstride, k, ri.p, rd.p, sm_count, s);
+  scatter_results<<<static_cast<unsigned>((uint64_t(m) * k + 255) / 256), 256, 0, s>>>(ri.p, rd.p, dw.p, m, k, d_out_ids, d_out_dist);
+  AB_CUDA(cudaGetLastError());
+  count_launch(2);
   AB_CUDA(cudaStreamSynchronize(s));
 }
 
 void bruteforce_topk_tc(int metric, const float *d_rows, uint64_t n, uint32_t dim, uint32_t stride, const float *d_queries,
                         uint64_t nq, uint32_t qstride, uint32_t k, uint32_t *d_out_ids, float *d_out_dist, int sm_count,
                         cudaStream_t s) {
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
   tc_run(metric, d_rows, n, dim, stride, d_queries, nq, qstride, k, d_out_ids, d_out_dist, sm_count, s, 0);
 }
 

@@ -193,7 +193,8 @@ void index_mark_workspace_use(ab_index *ix, cudaStream_t stream) {
 
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange, bool pad_empty) {
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange, bool pad_empty,
+                         const uint32_t *q_ready, uint32_t q_chunk) {
   AB_CHECK(ix->has_graph, AB_ERR_STATE, "index is not fitted or loaded");
   AB_CHECK(topk >= 1 && ef >= 1, AB_ERR_INVALID, "topk and ef must be positive");
   // the reference reads uninitialised pool slots when topk > ef (SURVEY.md 8b "Errors"); rejected here
@@ -261,6 +262,8 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   a.q_ids = nullptr;
   a.q_stride = ix->dim;
   a.q_prenormalized = 0;
+  a.q_ready = q_ready;
+  a.q_chunk = q_chunk;
   a.nq = static_cast<uint32_t>(nq);
   a.ef = ef;
   a.topk = topk;
@@ -326,10 +329,32 @@ static void search_host(ab_index *ix, const float *queries, uint64_t nq, uint32_
   uint32_t *d_ids = static_cast<uint32_t *>(mapped(out_ids));
   float *d_dist = out_dist ? static_cast<float *>(mapped(out_dist)) : nullptr;
   const bool stage_ids = d_ids == nullptr, stage_dist = out_dist != nullptr && d_dist == nullptr;
+  // Pageable queries: a plain cudaMemcpyAsync would serialise "stage + copy" in front of the kernel. For batches
+  // worth it the copy runs in chunks on a second stream WHILE the search kernel runs: the kernel is launched first,
+  // its warps pull queries in order and wait for the arrival flag of the chunk their query is in, which the copy
+  // engine writes right behind the chunk's data.
+  constexpr uint32_t kQueryChunks = 8;
+  const bool pipelined = d_q == nullptr && nq >= 2048 && pool_ids == nullptr;
+  uint32_t q_chunk = 0;
   if (d_q == nullptr) {
     ix->w_queries.reserve(nq * ix->dim);
-    AB_CUDA(cudaMemcpyAsync(ix->w_queries.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (!pipelined)
+      AB_CUDA(cudaMemcpyAsync(ix->w_queries.p, queries, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, s));
     d_q = ix->w_queries.p;
+  }
+  if (pipelined) {
+    if (ix->copy_stream == nullptr) {
+      AB_CUDA(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+      AB_CUDA(cudaEventCreateWithFlags(&ix->copy_event, cudaEventDisableTiming));
+      AB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ix->h_one), sizeof(uint32_t)));
+      *ix->h_one = 1u;
+    }
+    ix->w_qready.reserve(kQueryChunks);
+    q_chunk = static_cast<uint32_t>((nq + kQueryChunks - 1) / kQueryChunks);
+    index_order_after_searches(ix, s);  // the previous kernel may still be polling the old flags
+    AB_CUDA(cudaMemsetAsync(ix->w_qready.p, 0, kQueryChunks * sizeof(uint32_t), s));
+    AB_CUDA(cudaEventRecord(ix->copy_event, s));
+    AB_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->copy_event, 0));
   }
   if (stage_ids) {
     ix->w_ids.reserve(nq * topk);
@@ -346,7 +371,17 @@ static void search_host(ab_index *ix, const float *queries, uint64_t nq, uint32_
   }
   index_search_device(ix, d_q, nq, topk, ef, rerank, d_ids, out_dist ? d_dist : nullptr,
                       pool_ids ? ix->w_pool_ids.p : nullptr, pool_ids ? ix->w_pool_dist.p : nullptr,
-                      pool_ids ? ix->w_pool_sizes.p : nullptr, s);
+                      pool_ids ? ix->w_pool_sizes.p : nullptr, s, nullptr, false, pipelined ? ix->w_qready.p : nullptr, q_chunk);
+  if (pipelined) {
+    // the kernel is in flight; now feed it (each pageable copy returns once its chunk is staged)
+    for (uint32_t c = 0; c < kQueryChunks; c++) {
+      const uint64_t r0 = uint64_t(c) * q_chunk, r1 = std::min<uint64_t>(nq, r0 + q_chunk);
+      if (r0 < r1)
+        AB_CUDA(cudaMemcpyAsync(ix->w_queries.p + r0 * ix->dim, queries + r0 * ix->dim, (r1 - r0) * ix->dim * sizeof(float),
+                                cudaMemcpyHostToDevice, ix->copy_stream));
+      AB_CUDA(cudaMemcpyAsync(ix->w_qready.p + c, ix->h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, ix->copy_stream));
+    }
+  }
   if (stage_ids) AB_CUDA(cudaMemcpyAsync(out_ids, ix->w_ids.p, nq * topk * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   if (stage_dist) AB_CUDA(cudaMemcpyAsync(out_dist, ix->w_dist.p, nq * topk * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (pool_ids) {
@@ -432,6 +467,12 @@ void ab_index_destroy(ab_index *index) {
   if (index->ws_event) {
     cudaEventSynchronize(index->ws_event);
     cudaEventDestroy(index->ws_event);
+  }
+  if (index->copy_stream) {
+    cudaStreamSynchronize(index->copy_stream);
+    cudaStreamDestroy(index->copy_stream);
+    cudaEventDestroy(index->copy_event);
+    cudaFreeHost(index->h_one);
   }
   if (index->h_stats) cudaFreeHost(index->h_stats);
   delete index;
@@ -803,6 +844,7 @@ static void bruteforce_device_impl(int32_t metric, const float *d_data, uint64_t
     rows = pr.p;
     qs = pq.p;
   }
+  std::lock_guard<std::mutex> bf_lock(bruteforce_mutex());  // persistent workspaces of both paths
   if (bruteforce_tc_applicable(n, nq, k) && n >= k) {
     bruteforce_topk_tc(metric, rows, n, dim, stride, qs, nq, stride, k, d_out_ids, d_out_dist, sms, s);
   } else {

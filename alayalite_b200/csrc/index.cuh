@@ -14,6 +14,9 @@ struct ab_index {
   int sm_count = 148;
   size_t smem_limit = 227 * 1024;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host callers with pageable query buffers: chunked copy-in overlapped with the search
+  cudaEvent_t copy_event = nullptr;
+  uint32_t *h_one = nullptr;           // pinned constant 1 (source of the per-chunk "ready" flags)
   std::mutex mu;
 
   // ---- spaces (device) -----------------------------------------------------------------------
@@ -57,6 +60,7 @@ struct ab_index {
   ab::DevBuf<uint32_t> w_pool_ids, w_pool_sizes;
   ab::DevBuf<float> w_pool_dist;
   ab::DevBuf<uint32_t> w_counter;            // [1]
+  ab::DevBuf<uint32_t> w_qready;             // [kQueryChunks] per-chunk arrival flags of a pipelined copy-in
   ab::DevBuf<unsigned long long> w_stats;    // [8] device counters of the last launch (SearchArgs::stats)
   ab::VisitedWorkspace w_visited;            // overflow tables + pooled bitmaps of the visited set
   // {ndc, hops, overlay ndc, overflow-table queries, queries, bitmap queries, ids put into overflow tables}
@@ -90,7 +94,8 @@ uint64_t index_lists_len(const ab_index *ix);
 // d_queries / outputs are device pointers. cand/pool outputs optional.
 void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint32_t topk, uint32_t ef, bool rerank,
                          uint32_t *d_out_ids, float *d_out_dist, uint32_t *d_pool_ids, float *d_pool_dist,
-                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange = nullptr, bool pad_empty = false);
+                         uint32_t *d_pool_sizes, cudaStream_t stream, const Exchange *exchange = nullptr, bool pad_empty = false,
+                         const uint32_t *q_ready = nullptr, uint32_t q_chunk = 0);
 void index_save(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_load(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_build_graph(ab_index *ix, uint32_t ef_construction);

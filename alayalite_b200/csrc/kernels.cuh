@@ -1,5 +1,7 @@
 // Host-side launchers of the stand-alone kernels (quant.cu, bruteforce.cu, merge in bruteforce.cu).
 #pragma once
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ab {
@@ -22,6 +24,9 @@ void distance_pairs(int metric, int quant, const uint8_t *d_x, const uint8_t *d_
 void bruteforce_topk(int metric, const float *d_rows, uint64_t n, uint32_t stride_floats, const float *d_queries,
                      uint64_t nq, uint32_t q_stride_floats, uint32_t k, uint32_t *d_out_ids, float *d_out_dist,
                      int sm_count, cudaStream_t s);
+// serialises the users of the persistent brute-force workspaces (both paths); results are stream-ordered on `s`,
+// the caller synchronises
+std::mutex &bruteforce_mutex();
 // bruteforce_tc.cu: tcgen05 TF32 filter + exact re-evaluation (same contract and result as bruteforce_topk)
 bool bruteforce_tc_applicable(uint64_t n, uint64_t nq, uint32_t k);
 void bruteforce_topk_tc(int metric, const float *d_rows, uint64_t n, uint32_t dim, uint32_t stride_floats, const float *d_queries,

@@ -203,9 +203,11 @@ SearchPlan plan_search(int quant, int nchunks, int table_len, float visit_ratio,
   if (deep_on && quant == AB_QUANT_NONE && (nchunks == 24 || nchunks == 32)) {
     const int cap = nchunks == 24 ? 16 : 12, wpc = nchunks == 24 ? 8 : 6;
     const int have = p.warps_per_cta * p.ctas_per_sm;
-    if (deep_on == 2 || have <= cap) {
+    // small batches (every query has a warp of its own anyway): latency per hop is all that matters
+    const bool small_batch = nq <= static_cast<uint32_t>(sm_count) * static_cast<uint32_t>(cap);
+    if (deep_on == 2 || have <= cap || small_batch) {
       SearchPlan d = plan_search_impl(quant, nchunks, table_len, visit_ratio, ef, nq, n_rows, sm_count, smem_limit, min_warp_bytes, cap, wpc);
-      if (deep_on == 2 || 2 * d.warps_per_cta * d.ctas_per_sm > have + have / 4) {
+      if (deep_on == 2 || small_batch || 2 * d.warps_per_cta * d.ctas_per_sm > have + have / 4) {
         d.deep = 1;
         return d;
       }

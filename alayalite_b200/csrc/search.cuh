@@ -31,6 +31,11 @@ struct SearchArgs {
   const uint32_t *q_ids;  // optional indirection (graph build: the queries are base rows)
   size_t q_stride;        // floats between consecutive query rows
   int q_prenormalized;    // COS only: queries are stored rows, already normalised
+  // Host callers with pageable buffers: the queries are still arriving in chunks of q_chunk rows over a copy stream
+  // while this kernel runs; chunk c is complete once q_ready[c] != 0 (written by the copy engine behind the data).
+  // null = everything is there.
+  const uint32_t *q_ready;
+  uint32_t q_chunk;
   uint32_t nq;
   uint32_t ef, topk;
   // outputs: first topk pool entries (ids 0 / dist 0 past the pool size, like the reference's

@@ -608,6 +608,16 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
     __syncwarp();
     if (qi >= a.nq) break;
     const float *qg = a.queries + size_t(a.q_ids ? a.q_ids[qi] : qi) * a.q_stride;
+    if (a.q_ready != nullptr) {
+      // the query batch is still being copied in (search_host, pageable caller buffers): wait for this query's chunk
+      if (lane == 0) {
+        const volatile uint32_t *flag = a.q_ready + qi / a.q_chunk;
+        const long long t0 = clock64();
+        while (*flag == 0u && clock64() - t0 < 4000000000ll) __nanosleep(100);  // the time-out only guards against a failed copy
+        __threadfence();
+      }
+      __syncwarp();
+    }
 
     // ---- stage the query -------------------------------------------------------------------
     if (QUANT == AB_QUANT_NONE) {
@@ -615,7 +625,7 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
       const int nfl = a.nchunks * 4;
       float ss = 0.f;
       for (int i = lane; i < nfl; i += 32) {
-        const float x = i < static_cast<int>(a.dim) ? qg[i] : 0.f;
+        const float x = i < static_cast<int>(a.dim) ? __ldcg(qg + i) : 0.f;  // read at L2: the batch may still be arriving
         ws.q_raw[i] = x;
         ss = fmaf(x, x, ss);
       }
@@ -631,7 +641,7 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
       const int nb = a.nchunks * 16;
       for (int i = lane; i < nb; i += 32) {
         uint32_t c = 0;
-        if (i < static_cast<int>(a.dim)) c = sq_quantize(qg[i], a.qmin[i], a.qmax[i], 255.f);
+        if (i < static_cast<int>(a.dim)) c = sq_quantize(__ldcg(qg + i), a.qmin[i], a.qmax[i], 255.f);
         ws.q_code[i] = static_cast<uint8_t>(c);
       }
     } else {
@@ -640,8 +650,8 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
       for (int j = lane; j < nb; j += 32) {
         uint32_t first = 0, second = 0;
         const int i = 2 * j;
-        if (i < static_cast<int>(a.dim)) first = sq_quantize(qg[i], a.qmin[i], a.qmax[i], 15.f);
-        if (i + 1 < static_cast<int>(a.dim)) second = sq_quantize(qg[i + 1], a.qmin[i + 1], a.qmax[i + 1], 15.f);
+        if (i < static_cast<int>(a.dim)) first = sq_quantize(__ldcg(qg + i), a.qmin[i], a.qmax[i], 15.f);
+        if (i + 1 < static_cast<int>(a.dim)) second = sq_quantize(__ldcg(qg + i + 1), a.qmin[i + 1], a.qmax[i + 1], 15.f);
         ws.q_code[j] = static_cast<uint8_t>((first << 4) | second);
       }
     }
