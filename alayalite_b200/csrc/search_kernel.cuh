@@ -59,13 +59,15 @@ __device__ __forceinline__ uint32_t *ovf_slot(const SearchArgs &a) {
 
 // Level 3 of the visited set: claim one of the pooled N-bit bitmaps (rare: a query that fills its overflow table).
 // Warps wait for a free one; holders always finish on their own, so this cannot deadlock.
-__device__ __noinline__ int visit_claim_bitmap(const SearchArgs &a) {
+// (Out-of-line helpers take the few values they need, not the argument block: a reference to the kernel parameters
+// would force every thread to copy the whole block to local memory at kernel entry.)
+__device__ __noinline__ int visit_claim_bitmap(uint32_t *big_flags, uint32_t n_big) {
   int got = 0;
   if ((threadIdx.x & 31) == 0) {
-    uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % a.n_big, tries = 0;
-    while (atomicCAS(&a.big_flags[i], 0u, 1u) != 0u) {
-      i = i + 1 == a.n_big ? 0u : i + 1;
-      if (++tries >= a.n_big) {
+    uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % n_big, tries = 0;
+    while (atomicCAS(&big_flags[i], 0u, 1u) != 0u) {
+      i = i + 1 == n_big ? 0u : i + 1;
+      if (++tries >= n_big) {
         __nanosleep(2000);
         tries = 0;
       }
@@ -84,7 +86,7 @@ __device__ __forceinline__ bool visit_overflow(const SearchArgs &a, Visited &vs,
   uint32_t *tab = ovf_slot(a);
   const uint32_t mask = a.ovf_size - 1;
   const int lane = threadIdx.x & 31;
-  if (vs.big < 0 && vs.listed + 32 > a.ovf_limit) vs.big = visit_claim_bitmap(a);
+  if (vs.big < 0 && vs.listed + 32 > a.ovf_limit) vs.big = visit_claim_bitmap(a.big_flags, a.n_big);
   bool is_new = false, pending = want, to_big = false;
   uint32_t slot = (key * 0x85EBCA6Bu) & mask, mine = 0;
   while (__any_sync(kFull, pending)) {
@@ -122,22 +124,22 @@ __device__ __forceinline__ bool visit_overflow(const SearchArgs &a, Visited &vs,
 }
 
 // give the overflow table (and a claimed bitmap) back clean
-__device__ __noinline__ void visit_overflow_release(const SearchArgs &a, Visited &vs) {
-  uint32_t *tab = ovf_slot(a);
+__device__ __noinline__ void visit_overflow_release(uint32_t *tab, uint32_t ovf_size, uint32_t listed, int big_slot, uint32_t *big,
+                                                    size_t big_words, uint32_t *big_flags) {
   const int lane = threadIdx.x & 31;
   __syncwarp();
-  if (vs.listed <= kSpillList) {
-    for (uint32_t i = lane; i < vs.listed; i += 32) tab[tab[a.ovf_size + i]] = kEmptyId;
+  if (listed <= kSpillList) {
+    for (uint32_t i = lane; i < listed; i += 32) tab[tab[ovf_size + i]] = kEmptyId;
   } else {
     uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-    for (uint32_t w = lane; w < a.ovf_size / 4; w += 32) t4[w] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
+    for (uint32_t w = lane; w < ovf_size / 4; w += 32) t4[w] = make_uint4(kEmptyId, kEmptyId, kEmptyId, kEmptyId);
   }
-  if (vs.big >= 0) {
-    uint4 *bm = reinterpret_cast<uint4 *>(a.big + size_t(vs.big) * a.big_words);
-    for (size_t w = lane; w < a.big_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
+  if (big_slot >= 0) {
+    uint4 *bm = reinterpret_cast<uint4 *>(big + size_t(big_slot) * big_words);
+    for (size_t w = lane; w < big_words / 4; w += 32) bm[w] = make_uint4(0, 0, 0, 0);
     __threadfence();
     __syncwarp();
-    if (lane == 0) atomicExch(&a.big_flags[vs.big], 0u);
+    if (lane == 0) atomicExch(&big_flags[big_slot], 0u);
   }
   __syncwarp();
 }
@@ -838,7 +840,7 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
       exchange_epilogue(a.exchange, qi, a.topk, min(static_cast<uint32_t>(size), a.topk), a.out_ids + size_t(qi) * a.topk,
                         a.out_dist + size_t(qi) * a.topk, reinterpret_cast<uint2 *>(wbase), lane);
     }
-    if (vs.ovf_used) visit_overflow_release(a, vs);
+    if (vs.ovf_used) visit_overflow_release(ovf_slot(a), a.ovf_size, vs.listed, vs.big, a.big, a.big_words, a.big_flags);
     if (lane == 0) {
       atomicAdd(&a.stats[0], static_cast<unsigned long long>(ndc));
       atomicAdd(&a.stats[1], static_cast<unsigned long long>(hops));
