@@ -24,7 +24,7 @@ SYMBOLS = [
     "ab_index_get_dim", "ab_index_get_size", "ab_index_save", "ab_index_load", "ab_index_batch_search_device",
     "ab_quant_minmax", "ab_index_fit_ranged", "ab_group_create", "ab_group_destroy", "ab_group_fit", "ab_group_batch_search",
     "ab_group_index", "ab_comm_create", "ab_comm_connect", "ab_comm_batch_search_device", "ab_comm_errors", "ab_comm_destroy",
-    "ab_index_fit_spaces", "ab_index_set_graph", "ab_index_build_graph", "ab_index_graph_info", "ab_index_get_graph",
+    "ab_index_fit_spaces", "ab_index_set_graph", "ab_index_build_graph", "ab_index_build_graph_nsg", "ab_index_knng_nndescent", "ab_index_graph_info", "ab_index_get_graph",
     "ab_index_get_codes", "ab_index_search_stats", "ab_index_search_stats_ex", "ab_index_batch_traverse", "ab_distance_pairs", "ab_quant_fit_encode",
     "ab_normalize_rows", "ab_bruteforce_topk", "ab_bruteforce_topk_device", "ab_merge_topk_device", "ab_last_error",
     "ab_device_count", "ab_set_device", "ab_kernel_launch_count", "ab_version", "ab_debug_search_plan",
@@ -145,6 +145,14 @@ class NativeIndex:
 
     def build_graph(self, ef_construction=100):
         check(lib().ab_index_build_graph(self.h, C.c_uint32(ef_construction)))
+
+    def build_graph_nsg(self, ef_construction=100, nndescent_iters=10):
+        check(lib().ab_index_build_graph_nsg(self.h, C.c_uint32(ef_construction), C.c_uint32(nndescent_iters)))
+
+    def knng_nndescent(self, k=32, iters=10):
+        out = np.zeros((self.size, 32), np.uint32)
+        check(lib().ab_index_knng_nndescent(self.h, C.c_uint32(k), C.c_uint32(iters), _p(out, u32p)))
+        return out
 
     def set_graph(self, adj, levels, lists_flat, ep):
         adj = np.ascontiguousarray(adj, np.uint32)

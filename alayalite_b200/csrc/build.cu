@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <numeric>
@@ -150,7 +151,7 @@ template <bool IP, int TPV>
 __global__ void __launch_bounds__(128) reverse_kernel(const LayerView L, const uint32_t *__restrict__ sorted_dst,
                                                       const uint32_t *__restrict__ sorted_idx,
                                                       const uint32_t *__restrict__ edge_src,
-                                                      const float *__restrict__ edge_dist, uint32_t nedges) {
+                                                      const float *__restrict__ edge_dist, uint32_t nedges, int dedupe) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   uint8_t *wb = smem + size_t(warp) * build_warp_smem(L.nchunks);
@@ -168,10 +169,10 @@ __global__ void __launch_bounds__(128) reverse_kernel(const LayerView L, const u
     const uint32_t r = sorted_dst[i];
     if (r == kEmptyId || (i > 0 && sorted_dst[i - 1] == r)) continue;  // only segment heads work
     const uint32_t same = __ballot_sync(kFull, i + lane < nedges && sorted_dst[i + lane] == r);
-    const int inc = min(__ffs(~same) - 1 < 0 ? 32 : __ffs(~same) - 1, kMaxIncoming);
+    const int inc0 = min(__ffs(~same) - 1 < 0 ? 32 : __ffs(~same) - 1, kMaxIncoming);
     uint32_t pj = 0;
     float dj = 0.f;
-    if (lane < inc) {
+    if (lane < inc0) {
       const uint32_t e = sorted_idx[i + lane];
       pj = edge_src[e];
       dj = edge_dist[e];
@@ -179,6 +180,27 @@ __global__ void __launch_bounds__(128) reverse_kernel(const LayerView L, const u
     const uint32_t cur = L.adj[size_t(r) * kR + lane];
     const uint32_t empties = __ballot_sync(kFull, cur == kEmptyId);
     const int cnt = empties ? __ffs(empties) - 1 : kR;
+    int inc = inc0;
+    if (dedupe) {
+      // NSG (add_reverse_links, nsg_builder.hpp:462-470): r may already link to the source (mutual edge), and a source
+      // never links to itself; HNSW inserts never meet either case (the new point is in nobody's row yet)
+      bool drop = lane >= inc0 || pj == r;
+      for (int j = 0; j < cnt; j++) drop |= __shfl_sync(kFull, cur, j) == pj;
+      const uint32_t keep = __ballot_sync(kFull, !drop);
+      inc = __popc(keep);
+      if (!drop) {
+        const int at = __popc(keep & ((1u << lane) - 1));
+        sid[at] = pj;
+        sd[at] = dj;
+      }
+      __syncwarp();
+      if (lane < inc) {
+        pj = sid[lane];
+        dj = sd[lane];
+      }
+      __syncwarp();
+      if (inc == 0) continue;
+    }
     if (cnt + inc <= static_cast<int>(L.mmax)) {  // hnswlib.hpp:594-597: room left -> append
       if (lane < inc) L.adj[size_t(r) * kR + cnt + lane] = pj;
       continue;
@@ -272,7 +294,7 @@ void launch_select(int tpv, const LayerView &L, const uint32_t *batch_ids, uint3
 }
 
 template <bool IP>
-void launch_reverse(int tpv, const LayerView &L, Workspace &w, uint32_t nedges, int sms, cudaStream_t s) {
+void launch_reverse(int tpv, const LayerView &L, Workspace &w, uint32_t nedges, int sms, cudaStream_t s, int dedupe = 0) {
   const int warps = 4;
   const size_t smem = build_warp_smem(L.nchunks) * warps;
   const int blocks = std::max(1, std::min<int>((nedges + warps - 1) / warps, sms * 16));
@@ -280,7 +302,7 @@ void launch_reverse(int tpv, const LayerView &L, Workspace &w, uint32_t nedges, 
   {                                                                                                        \
     auto k = reverse_kernel<IP, T>;                                                                        \
     AB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-    k<<<blocks, warps * 32, smem, s>>>(L, w.sorted_dst.p, w.sorted_idx.p, w.edge_src.p, w.edge_dist.p, nedges); \
+    k<<<blocks, warps * 32, smem, s>>>(L, w.sorted_dst.p, w.sorted_idx.p, w.edge_src.p, w.edge_dist.p, nedges, dedupe); \
   }
   switch (tpv) {
     case 4: AB_REV(4); break;
@@ -503,6 +525,671 @@ void index_build_graph(ab_index *ix, uint32_t ef_construction) {
   ix->has_overlay = true;
   ix->has_graph = true;
   std::copy(levels.begin(), levels.end(), ix->h_levels.begin());
+  std::fill(ix->h_valid_graph.begin(), ix->h_valid_graph.begin() + n, 1);
+}
+
+
+// =====================================================================================================================
+// NN-Descent k-NN graph + NSG. Replaces, on the device (paths relative to /root/reference):
+//   NndescentImpl::init_graph / join / update / build_graph   include/index/graph/knng/nndescent.hpp:142-400
+//   NSGBuilder::build_graph / init / link / sync_prune / add_reverse_links / tree_grow
+//                                                              include/index/graph/nsg/nsg_builder.hpp:97-560
+// Only reachable from C++ in the reference (its Python path builds HNSW for every index type), hence a separate entry
+// point (ab_index_build_graph_nsg) and no bit-level contract: the reference's own result depends on thread timing
+// and std::mt19937 streams. The bar is recall at equal ef against the reference's NSG (tests/test_gpu_nsg.py).
+//
+// NN-Descent, lock-free: every node keeps a pool of kNndPool nearest candidates sorted by distance, entries flagged
+// "new" until sampled. One iteration = (1) sample: per node the first S new and the old entries before them
+// (nndescent.hpp:318-338), reverse lists by radix sort of (neighbour, node) pairs instead of per-node locks, capped at
+// kNndRev per list (the reference keeps <= radius = 100 by random replacement); (2) local join: all new x new and
+// new x old pairs of a node's lists (Nhood::join), each distance evaluated once by a lane group, and every pair that
+// beats the current worst of either endpoint's pool becomes a proposal {target, candidate, distance}; (3) update:
+// proposals radix-sorted by target, one warp per target folds them into its pool (the reference's Nhood::insert
+// under a mutex). The k-NN graph is the first K = 32 entries of every pool.
+// NSG: navigating node = nearest stored row to the centroid (found by a traversal of the k-NN graph, init());
+// link() = for every node the candidates of a traversal of the k-NN graph from the navigating node at ef_construction
+// (beam_search_kernel, queries = stored rows) pruned with the MRNG rule to <= 32 edges (sync_prune == the heuristic of
+// select_kernel with limit 32), reverse edges grouped by target and re-pruned on overflow (add_reverse_links ==
+// reverse_kernel), in batches so that no row receives more than a few reverse edges per step; tree_grow() = a
+// breadth-first pass from the navigating node on the host, every unreached node attached to the nearest reached
+// neighbour of its own list.
+namespace {
+
+constexpr int kNndPool = 64;               // pool entries per node (the reference: K + 50 = 82)
+constexpr int kNndRev = 22;                // reverse entries folded into a node's new / old list per iteration
+constexpr uint32_t kNndIdMask = 0x7FFFFFFFu;
+constexpr uint32_t kNndNew = 0x80000000u;
+
+__host__ __device__ __forceinline__ uint32_t nnd_hash(uint32_t a, uint32_t b) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u);
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+// distance between two stored rows, one lane group of TPV lanes per pair; every lane of the group gets the sum
+template <bool IP, int TPV>
+__device__ __forceinline__ float pair_distance(const LayerView &L, uint32_t a, uint32_t b, int lg, bool act) {
+  float acc = 0.f;
+  if (act) {
+    const uint8_t *ra = L.rows + size_t(a) * L.stride, *rb = L.rows + size_t(b) * L.stride;
+    for (int c = lg; c < L.nchunks; c += TPV) {
+      const uint4 x = ldg128(ra + size_t(c) * 16), y = ldg128(rb + size_t(c) * 16);
+      const float x0 = __uint_as_float(x.x), x1 = __uint_as_float(x.y), x2 = __uint_as_float(x.z), x3 = __uint_as_float(x.w);
+      const float y0 = __uint_as_float(y.x), y1 = __uint_as_float(y.y), y2 = __uint_as_float(y.z), y3 = __uint_as_float(y.w);
+      if (IP) {
+        acc = fmaf(x0, y0, acc);
+        acc = fmaf(x1, y1, acc);
+        acc = fmaf(x2, y2, acc);
+        acc = fmaf(x3, y3, acc);
+      } else {
+        const float d0 = x0 - y0, d1 = x1 - y1, d2 = x2 - y2, d3 = x3 - y3;
+        acc = fmaf(d0, d0, acc);
+        acc = fmaf(d1, d1, acc);
+        acc = fmaf(d2, d2, acc);
+        acc = fmaf(d3, d3, acc);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = TPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  return IP ? -acc : acc;
+}
+
+// init_graph (nndescent.hpp:178-219): pseudo-random neighbours, sorted, all flagged new. The pool is filled completely
+// (64 draws, duplicates dropped) so that its worst distance filters proposals from the first iteration on.
+template <bool IP>
+__global__ void __launch_bounds__(128) nnd_init_kernel(const LayerView L, uint32_t n, uint32_t seed, uint2 *__restrict__ pool) {
+  __shared__ uint2 s_e[4][kNndPool];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint2 *E = s_e[warp];
+  for (uint32_t v = blockIdx.x * warps + warp; v < n; v += gridDim.x * warps) {
+    for (int h = 0; h < 2; h++) {
+      uint32_t id = nnd_hash(v * 64u + h * 32u + lane, seed) % n;
+      if (id == v) id = id + 1 == n ? 0u : id + 1;
+      float d = FLT_MAX;
+      for (int j = 0; j < 32; j++) {  // every lane's pair in turn, the whole warp on one pair
+        const uint32_t b = __shfl_sync(kFull, id, j);
+        const float dj = pair_distance<IP, 32>(L, v, b, lane, true);
+        if (lane == j) d = dj;
+      }
+      E[h * 32 + lane] = make_uint2(__float_as_uint(d), id);
+    }
+    __syncwarp();
+    uint2 *row = pool + size_t(v) * kNndPool;
+    for (int h = 0; h < 2; h++) {
+      const int me = h * 32 + lane;
+      uint2 e = E[me];
+      bool dup = false;
+      for (int j = 0; j < me; j++) dup |= E[j].y == e.y;
+      if (dup) e = make_uint2(__float_as_uint(FLT_MAX), kNndIdMask);
+      E[me] = e;  // (lanes only read entries below their own, which are final by the time a later entry's flag matters)
+    }
+    __syncwarp();
+    for (int h = 0; h < 2; h++) {
+      const int me = h * 32 + lane;
+      const uint2 e = E[me];
+      const float d = __uint_as_float(e.x);
+      int rank = 0;
+      for (int j = 0; j < kNndPool; j++) {
+        const uint2 o = E[j];
+        const float dj = __uint_as_float(o.x);
+        rank += (dj < d || (dj == d && (o.y < e.y || (o.y == e.y && j < me)))) ? 1 : 0;
+      }
+      row[rank] = e.y == kNndIdMask ? e : make_uint2(e.x, e.y | kNndNew);
+    }
+    __syncwarp();
+  }
+}
+
+// update(), first half: sample the lists of every node and emit the reverse pairs
+__global__ void __launch_bounds__(128) nnd_sample_kernel(uint32_t n, uint32_t S, uint2 *__restrict__ pool, uint32_t *__restrict__ nn_new,
+                                                         uint32_t *__restrict__ nn_old, uint32_t *__restrict__ rkey_new,
+                                                         uint32_t *__restrict__ rval_new, uint32_t *__restrict__ rkey_old,
+                                                         uint32_t *__restrict__ rval_old) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (uint32_t v = blockIdx.x * warps + warp; v < n; v += gridDim.x * warps) {
+    uint2 *row = pool + size_t(v) * kNndPool;
+    uint2 e[2] = {row[lane], row[lane + 32]};
+    const bool valid[2] = {(e[0].y & kNndIdMask) != kNndIdMask, (e[1].y & kNndIdMask) != kNndIdMask};
+    const uint32_t newm[2] = {__ballot_sync(kFull, valid[0] && (e[0].y & kNndNew)), __ballot_sync(kFull, valid[1] && (e[1].y & kNndNew))};
+    const uint32_t oldm[2] = {__ballot_sync(kFull, valid[0] && !(e[0].y & kNndNew)), __ballot_sync(kFull, valid[1] && !(e[1].y & kNndNew))};
+    const uint32_t lt = (1u << lane) - 1;
+    for (int i = lane; i < static_cast<int>(S); i += 32) {  // empty lists first, entries below
+      nn_new[size_t(v) * S + i] = kEmptyId;
+      rkey_new[size_t(v) * S + i] = kEmptyId;
+      rval_new[size_t(v) * S + i] = v;
+      nn_old[size_t(v) * S + i] = kEmptyId;
+      rkey_old[size_t(v) * S + i] = kEmptyId;
+      rval_old[size_t(v) * S + i] = v;
+    }
+    __syncwarp();
+    for (int h = 0; h < 2; h++) {
+      // rank among the new / old entries in pool order
+      const int nrank = (h ? __popc(newm[0]) : 0) + __popc(newm[h] & lt);
+      const int orank = (h ? __popc(oldm[0]) : 0) + __popc(oldm[h] & lt);
+      const bool is_new = valid[h] && (e[h].y & kNndNew), is_old = valid[h] && !(e[h].y & kNndNew);
+      const uint32_t u = e[h].y & kNndIdMask;
+      // nndescent.hpp:329-337: the scan stops once S new entries were seen; old entries count only before that point
+      if (is_new && nrank < static_cast<int>(S)) {
+        nn_new[size_t(v) * S + nrank] = u;
+        // reverse list of u, only when v is farther than u's current worst (:365, :377)
+        const float worst_u = __uint_as_float(pool[size_t(u) * kNndPool + kNndPool - 1].x);
+        if (__uint_as_float(e[h].x) > worst_u) rkey_new[size_t(v) * S + nrank] = u;
+        row[lane + 32 * h].y = u;  // sampled: no longer new
+      }
+      if (is_old && nrank < static_cast<int>(S) && orank < static_cast<int>(S)) {
+        nn_old[size_t(v) * S + orank] = u;
+        const float worst_u = __uint_as_float(pool[size_t(u) * kNndPool + kNndPool - 1].x);
+        if (__uint_as_float(e[h].x) > worst_u) rkey_old[size_t(v) * S + orank] = u;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t m, uint32_t key) {
+  uint32_t lo = 0, hi = m;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// join() (nndescent.hpp:259-287) without locks: pairs -> proposals
+template <bool IP>
+__global__ void __launch_bounds__(128) nnd_join_kernel(const LayerView L, uint32_t n, uint32_t S, const uint32_t *__restrict__ nn_new,
+                                                       const uint32_t *__restrict__ nn_old, const uint32_t *__restrict__ skey_new,
+                                                       const uint32_t *__restrict__ sval_new, const uint32_t *__restrict__ skey_old,
+                                                       const uint32_t *__restrict__ sval_old, uint32_t m, const uint2 *__restrict__ pool,
+                                                       uint32_t *__restrict__ prop_key, unsigned long long *__restrict__ prop_val,
+                                                       uint32_t *__restrict__ prop_count, uint32_t prop_cap) {
+  __shared__ uint32_t s_lists[4][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  constexpr int TPV = 8, G = 4;
+  const int g = lane / TPV, lg = lane % TPV;
+  uint32_t *A = s_lists[warp][0], *B = s_lists[warp][1];
+  for (uint32_t v = blockIdx.x * warps + warp; v < n; v += gridDim.x * warps) {
+    // own samples first, then the head of the reverse segment
+    uint32_t a = lane < static_cast<int>(S) ? nn_new[size_t(v) * S + lane] : kEmptyId;
+    uint32_t b = lane < static_cast<int>(S) ? nn_old[size_t(v) * S + lane] : kEmptyId;
+    const uint32_t ra = lower_bound_u32(skey_new, m, v), rb = lower_bound_u32(skey_old, m, v);
+    if (lane >= static_cast<int>(S) && lane < static_cast<int>(S) + kNndRev) {
+      const uint32_t ia = ra + lane - S, ib = rb + lane - S;
+      if (ia < m && skey_new[ia] == v) a = sval_new[ia];
+      if (ib < m && skey_old[ib] == v) b = sval_old[ib];
+    }
+    // compact + drop duplicates (an id may arrive through both routes)
+    bool keep_a = a != kEmptyId && a != v, keep_b = b != kEmptyId && b != v;
+    for (int j = 0; j < 32; j++) {
+      const uint32_t aj = __shfl_sync(kFull, a, j), bj = __shfl_sync(kFull, b, j);
+      const bool ka = __shfl_sync(kFull, keep_a, j), kb = __shfl_sync(kFull, keep_b, j);
+      if (j < lane && ka && aj == a) keep_a = false;
+      if (j < lane && kb && bj == b) keep_b = false;
+      if (ka && aj == b) keep_b = false;  // already handled as a new neighbour
+    }
+    const uint32_t ma = __ballot_sync(kFull, keep_a), mb = __ballot_sync(kFull, keep_b);
+    const int na = __popc(ma), nb = __popc(mb);
+    if (keep_a) A[__popc(ma & ((1u << lane) - 1))] = a;
+    if (keep_b) B[__popc(mb & ((1u << lane) - 1))] = b;
+    __syncwarp();
+    for (int i = 0; i < na; i++) {
+      const uint32_t x = A[i];
+      const float worst_x = __uint_as_float(pool[size_t(x) * kNndPool + kNndPool - 1].x);
+      const int partners = (na - i - 1) + nb;  // A[i+1..) then B[0..)
+      for (int base = 0; base < partners; base += G) {
+        const int t = base + g;
+        const bool act = t < partners;
+        const uint32_t y = act ? (t < na - i - 1 ? A[i + 1 + t] : B[t - (na - i - 1)]) : x;
+        const float d = pair_distance<IP, TPV>(L, x, y, lg, act);
+        if (act && lg == 0 && x != y) {
+          const float worst_y = __uint_as_float(pool[size_t(y) * kNndPool + kNndPool - 1].x);
+          const bool to_x = d < worst_x, to_y = d < worst_y;
+          const uint32_t cnt = (to_x ? 1u : 0u) + (to_y ? 1u : 0u);
+          if (cnt) {
+            uint32_t pos = atomicAdd(prop_count, cnt);
+            if (to_x && pos < prop_cap) {
+              prop_key[pos] = x;
+              prop_val[pos] = (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | y;
+              pos++;
+            }
+            if (to_y && pos < prop_cap) {
+              prop_key[pos] = y;
+              prop_val[pos] = (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | x;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// update(), second half: one warp per target folds its proposals into the pool (Nhood::insert, nndescent.hpp:76-99)
+__global__ void __launch_bounds__(128) nnd_merge_kernel(const uint32_t *__restrict__ skey, const unsigned long long *__restrict__ sval,
+                                                        uint32_t m, uint2 *__restrict__ pool, unsigned long long *__restrict__ inserted) {
+  __shared__ uint2 s_pool[4][kNndPool + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint2 *P = s_pool[warp];
+  unsigned long long mine = 0;
+  for (uint32_t i = blockIdx.x * warps + warp; i < m; i += gridDim.x * warps) {
+    const uint32_t t = skey[i];
+    if (t == kEmptyId || (i > 0 && skey[i - 1] == t)) continue;  // only segment heads work
+    uint2 *row = pool + size_t(t) * kNndPool;
+    P[lane] = row[lane];
+    P[lane + 32] = row[lane + 32];
+    __syncwarp();
+    for (uint32_t j = i; j < m && skey[j] == t; j++) {
+      const unsigned long long pv = sval[j];
+      const float d = __uint_as_float(static_cast<uint32_t>(pv >> 32));
+      const uint32_t c = static_cast<uint32_t>(pv);
+      const uint2 e0 = P[lane], e1 = P[lane + 32];
+      if (!(d < __uint_as_float(P[kNndPool - 1].x))) continue;
+      const bool dup = __any_sync(kFull, (e0.y & kNndIdMask) == c || (e1.y & kNndIdMask) == c);
+      if (dup) continue;
+      const int pos = __popc(__ballot_sync(kFull, __uint_as_float(e0.x) <= d)) + __popc(__ballot_sync(kFull, __uint_as_float(e1.x) <= d));
+      __syncwarp();
+      if (lane >= pos && lane + 1 < kNndPool) P[lane + 1] = e0;
+      if (lane + 32 >= pos && lane + 33 < kNndPool) P[lane + 33] = e1;
+      if (lane == 0) P[pos] = make_uint2(__float_as_uint(d), c | kNndNew);
+      __syncwarp();
+      mine++;
+    }
+    row[lane] = P[lane];
+    row[lane + 32] = P[lane + 32];
+    __syncwarp();
+  }
+  if (lane == 0 && mine) atomicAdd(inserted, mine);
+}
+
+__global__ void nnd_export_kernel(const uint2 *__restrict__ pool, uint32_t n, uint32_t K, uint32_t *__restrict__ knng) {
+  const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= uint64_t(n) * kR) return;
+  const uint32_t v = static_cast<uint32_t>(t / kR), j = static_cast<uint32_t>(t % kR);
+  uint32_t id = kEmptyId;
+  if (j < K) {
+    const uint32_t e = pool[size_t(v) * kNndPool + j].y & kNndIdMask;
+    if (e != kNndIdMask) id = e;
+  }
+  knng[t] = id;
+}
+
+__global__ void centroid_kernel(const float *__restrict__ rows, uint32_t n, uint32_t dim, uint32_t stride, float *__restrict__ out) {
+  // one block per dimension slice: column means (NSGBuilder::init, nsg_builder.hpp:170-186)
+  const uint32_t d = blockIdx.x;
+  double acc = 0.0;
+  for (uint32_t r = threadIdx.x; r < n; r += blockDim.x) acc += rows[size_t(r) * stride + d];
+  __shared__ double part[256];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && d < dim) out[d] = static_cast<float>(part[0] / n);
+}
+
+// sync_prune (nsg_builder.hpp:370-430): candidates ascending by distance to p, p itself skipped, MRNG rule, <= 32 kept
+template <bool IP, int TPV>
+__global__ void __launch_bounds__(128) nsg_select_kernel(const LayerView L, const uint32_t *__restrict__ batch_ids, uint32_t B,
+                                                         const uint32_t *__restrict__ pool_ids, const float *__restrict__ pool_dist,
+                                                         const uint32_t *__restrict__ pool_sizes, uint32_t ef,
+                                                         uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ edge_src,
+                                                         float *__restrict__ edge_dist, uint32_t *__restrict__ cid_ws, float *__restrict__ cd_ws) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint8_t *wb = smem + size_t(warp) * build_warp_smem(L.nchunks);
+  float *q = reinterpret_cast<float *>(wb);
+  uint32_t *kept = reinterpret_cast<uint32_t *>(wb + size_t(L.nchunks) * 16);
+  float *kept_d = reinterpret_cast<float *>(kept + 32);
+  float *scratch = kept_d + 32;
+  for (uint32_t b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    const uint32_t p = batch_ids[b];
+    const int size = static_cast<int>(min(pool_sizes[b], ef));
+    // compact the pool without p (a stored row finds itself at distance 0)
+    uint32_t *cid = cid_ws + size_t(b) * ef;
+    float *cd = cd_ws + size_t(b) * ef;
+    int total = 0;
+    for (int base = 0; base < size; base += 32) {
+      const int i = base + lane;
+      const uint32_t id = i < size ? pool_ids[size_t(b) * ef + i] : p;
+      const bool keep = i < size && id != p;
+      const uint32_t km = __ballot_sync(kFull, keep);
+      if (keep) {
+        const int at = total + __popc(km & ((1u << lane) - 1));
+        cid[at] = id;
+        cd[at] = pool_dist[size_t(b) * ef + i];
+      }
+      total += __popc(km);
+    }
+    __syncwarp();
+    const int nkept = heuristic<IP, TPV>(L, q, cid, cd, total, kR, kept, kept_d, scratch, lane);
+    L.adj[size_t(p) * kR + lane] = lane < nkept ? kept[lane] : kEmptyId;
+    edge_dst[size_t(b) * kR + lane] = lane < nkept ? kept[lane] : kEmptyId;
+    edge_src[size_t(b) * kR + lane] = p;
+    edge_dist[size_t(b) * kR + lane] = lane < nkept ? kept_d[lane] : 0.f;
+    __syncwarp();
+  }
+}
+
+// out-edges of a batch of nodes with their lengths, as input of the reverse-link step
+template <bool IP>
+__global__ void __launch_bounds__(128) nsg_edges_kernel(const LayerView L, const uint32_t *__restrict__ batch_ids, uint32_t B,
+                                                        uint32_t *__restrict__ edge_dst, uint32_t *__restrict__ edge_src,
+                                                        float *__restrict__ edge_dist) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (uint32_t b = blockIdx.x * warps + warp; b < B; b += gridDim.x * warps) {
+    const uint32_t p = batch_ids[b];
+    const uint32_t dst = L.adj[size_t(p) * kR + lane];
+    float d = 0.f;
+    for (int j = 0; j < kR; j++) {
+      const uint32_t y = __shfl_sync(kFull, dst, j);
+      if (y == kEmptyId) break;  // rows are compact from the left
+      const float dj = pair_distance<IP, 32>(L, p, y, lane, true);
+      if (lane == j) d = dj;
+    }
+    edge_dst[size_t(b) * kR + lane] = dst;
+    edge_src[size_t(b) * kR + lane] = p;
+    edge_dist[size_t(b) * kR + lane] = d;
+    __syncwarp();
+  }
+}
+
+struct NsgWorkspace {
+  DevBuf<uint2> pool;
+  DevBuf<uint32_t> nn_new, nn_old, rk_new, rv_new, rk_old, rv_old, sk_new, sv_new, sk_old, sv_old, prop_key, prop_skey, counter, knng;
+  DevBuf<unsigned long long> prop_val, prop_sval, inserted;
+  DevBuf<uint8_t> cub_tmp;
+};
+
+void search_rows_on_graph(ab_index *ix, const LayerView &view, const uint32_t *d_adj, const float *d_queries, const uint32_t *q_ids,
+                          size_t q_stride, uint32_t nq, uint32_t ef, uint32_t ep, Workspace &w, bool ip, cudaStream_t s) {
+  SearchPlan plan = plan_search(AB_QUANT_NONE, view.nchunks, 0, 1.2f, ef, nq, static_cast<uint32_t>(ix->n), ix->sm_count, ix->smem_limit);
+  w.visited.prepare(plan, ix->n, s);
+  AB_CUDA(cudaMemsetAsync(w.counter.p, 0, sizeof(uint32_t), s));
+  SearchArgs a{};
+  a.rows = view.rows;
+  a.row_stride = static_cast<uint32_t>(view.stride);
+  a.nchunks = view.nchunks;
+  a.adj = d_adj;
+  a.ov_off = nullptr;
+  a.ov_lists = nullptr;
+  a.valid = nullptr;
+  a.ep = ep;
+  a.ep_level = 0;
+  a.n = static_cast<uint32_t>(ix->n);
+  a.dim = ix->dim;
+  a.metric = ip ? AB_METRIC_IP : AB_METRIC_L2;
+  a.queries = d_queries;
+  a.q_ids = q_ids;
+  a.q_stride = q_stride;
+  a.q_prenormalized = 1;
+  a.nq = nq;
+  a.ef = ef;
+  a.topk = 1;
+  a.out_ids = w.first.p;
+  a.out_dist = nullptr;
+  a.pool_ids = w.pool_ids.p;
+  a.pool_dist = w.pool_dist.p;
+  a.pool_sizes = w.pool_sizes.p;
+  a.work_counter = w.counter.p;
+  a.hash_size = plan.hash_size;
+  w.visited.fill(a);
+  a.stats = w.stats.p;
+  launch_search(AB_QUANT_NONE, plan, a, s);
+}
+
+}  // namespace
+
+// NndescentImpl::build_graph on the device: knng [n, 32] (0xFFFFFFFF padded) in `W.knng`
+static void nndescent_build(ab_index *ix, uint32_t K, uint32_t S, uint32_t iters, NsgWorkspace &W, bool ip, std::vector<double> *trace) {
+  cudaStream_t s = ix->stream;
+  const uint32_t n = static_cast<uint32_t>(ix->n);
+  const LayerView view{reinterpret_cast<const uint8_t *>(ix->raw.p), size_t(ix->raw_stride) * 4, ix->raw_chunks, nullptr, kR};
+  const size_t m = size_t(n) * S;
+  W.pool.reserve(size_t(n) * kNndPool);
+  for (DevBuf<uint32_t> *b : {&W.nn_new, &W.nn_old, &W.rk_new, &W.rv_new, &W.rk_old, &W.rv_old, &W.sk_new, &W.sv_new, &W.sk_old, &W.sv_old}) b->reserve(m);
+  // proposals: each node can emit thousands of pairs in the first iterations; whatever does not fit is dropped (the
+  // next iteration sees the same neighbourhoods again), like the reference drops updates that lose the race for a lock
+  const size_t prop_cap = std::min<size_t>(size_t(n) * 96, size_t(1) << 30);
+  W.prop_key.reserve(prop_cap);
+  W.prop_skey.reserve(prop_cap);
+  W.prop_val.reserve(prop_cap);
+  W.prop_sval.reserve(prop_cap);
+  W.counter.reserve(1);
+  W.inserted.reserve(1);
+  W.knng.reserve(size_t(n) * kR);
+  size_t cub_a = 0, cub_b = 0;
+  AB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_a, W.rk_new.p, W.sk_new.p, W.rv_new.p, W.sv_new.p, static_cast<int>(m), 0, 32, s));
+  AB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_b, W.prop_key.p, W.prop_skey.p, W.prop_val.p, W.prop_sval.p,
+                                          static_cast<int>(std::min<size_t>(prop_cap, 0x7FFFFFFF)), 0, 32, s));
+  W.cub_tmp.reserve(std::max(cub_a, cub_b) + 16);
+  const int grid = ix->sm_count * 8;
+  if (ip) nnd_init_kernel<true><<<grid, 128, 0, s>>>(view, n, 347u * 6007u, W.pool.p);
+  else nnd_init_kernel<false><<<grid, 128, 0, s>>>(view, n, 347u * 6007u, W.pool.p);
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+  for (uint32_t it = 0; it < iters; it++) {
+    nnd_sample_kernel<<<grid, 128, 0, s>>>(n, S, W.pool.p, W.nn_new.p, W.nn_old.p, W.rk_new.p, W.rv_new.p, W.rk_old.p, W.rv_old.p);
+    AB_CUDA(cudaGetLastError());
+    size_t tmp = W.cub_tmp.n;
+    AB_CUDA(cub::DeviceRadixSort::SortPairs(W.cub_tmp.p, tmp, W.rk_new.p, W.sk_new.p, W.rv_new.p, W.sv_new.p, static_cast<int>(m), 0, 32, s));
+    tmp = W.cub_tmp.n;
+    AB_CUDA(cub::DeviceRadixSort::SortPairs(W.cub_tmp.p, tmp, W.rk_old.p, W.sk_old.p, W.rv_old.p, W.sv_old.p, static_cast<int>(m), 0, 32, s));
+    AB_CUDA(cudaMemsetAsync(W.counter.p, 0, 4, s));
+    if (ip)
+      nnd_join_kernel<true><<<grid, 128, 0, s>>>(view, n, S, W.nn_new.p, W.nn_old.p, W.sk_new.p, W.sv_new.p, W.sk_old.p, W.sv_old.p,
+                                                 static_cast<uint32_t>(m), W.pool.p, W.prop_key.p, W.prop_val.p, W.counter.p,
+                                                 static_cast<uint32_t>(std::min<size_t>(prop_cap, 0xFFFFFFF0u)));
+    else
+      nnd_join_kernel<false><<<grid, 128, 0, s>>>(view, n, S, W.nn_new.p, W.nn_old.p, W.sk_new.p, W.sv_new.p, W.sk_old.p, W.sv_old.p,
+                                                  static_cast<uint32_t>(m), W.pool.p, W.prop_key.p, W.prop_val.p, W.counter.p,
+                                                  static_cast<uint32_t>(std::min<size_t>(prop_cap, 0xFFFFFFF0u)));
+    AB_CUDA(cudaGetLastError());
+    uint32_t nprop = 0;
+    AB_CUDA(cudaMemcpyAsync(&nprop, W.counter.p, 4, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(cudaStreamSynchronize(s));
+    nprop = static_cast<uint32_t>(std::min<size_t>(nprop, prop_cap));
+    count_launch(4);
+    unsigned long long ins = 0;
+    if (nprop > 0) {
+      tmp = W.cub_tmp.n;
+      AB_CUDA(cub::DeviceRadixSort::SortPairs(W.cub_tmp.p, tmp, W.prop_key.p, W.prop_skey.p, W.prop_val.p, W.prop_sval.p, static_cast<int>(nprop), 0,
+                                              32, s));
+      AB_CUDA(cudaMemsetAsync(W.inserted.p, 0, 8, s));
+      nnd_merge_kernel<<<grid * 2, 128, 0, s>>>(W.prop_skey.p, W.prop_sval.p, nprop, W.pool.p, W.inserted.p);
+      AB_CUDA(cudaGetLastError());
+      AB_CUDA(cudaMemcpyAsync(&ins, W.inserted.p, 8, cudaMemcpyDeviceToHost, s));
+      AB_CUDA(cudaStreamSynchronize(s));
+      count_launch(2);
+    }
+    if (trace) trace->push_back(double(ins) / double(n));
+    if (ins < n / 1000) break;  // converged: fewer than 0.001 pool updates per node
+  }
+  nnd_export_kernel<<<static_cast<unsigned>((uint64_t(n) * kR + 255) / 256), 256, 0, s>>>(W.pool.p, n, K, W.knng.p);
+  AB_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void index_knng_nndescent(ab_index *ix, uint32_t K, uint32_t iters, uint32_t *out_ids) {
+  const uint32_t n = static_cast<uint32_t>(ix->n);
+  AB_CHECK(n > 64 && ix->n_raw == ix->n, AB_ERR_STATE, "fit the spaces first (at least 65 rows)");
+  AB_CHECK(K >= 1 && K <= 32, AB_ERR_INVALID, "K must be in [1, 32]");
+  NsgWorkspace W;
+  nndescent_build(ix, K, 10, iters, W, ix->params.metric != AB_METRIC_L2, nullptr);
+  AB_CUDA(cudaMemcpyAsync(out_ids, W.knng.p, size_t(n) * kR * 4, cudaMemcpyDeviceToHost, ix->stream));
+  AB_CUDA(cudaStreamSynchronize(ix->stream));
+}
+
+void index_build_graph_nsg(ab_index *ix, uint32_t ef_construction, uint32_t nnd_iters) {
+  cudaStream_t s = ix->stream;
+  static const bool debug = getenv("AB_NSG_DEBUG") != nullptr;
+  auto stage = [&](const char *what) {  // developer aid: localise a faulting kernel
+    if (!debug) return;
+    const cudaError_t e = cudaStreamSynchronize(s);
+    std::fprintf(stderr, "[nsg] %s: %s\n", what, cudaGetErrorString(e));
+    if (e != cudaSuccess) throw Error(AB_ERR_CUDA, std::string("NSG build failed at ") + what + ": " + cudaGetErrorString(e));
+  };
+  const uint32_t n = static_cast<uint32_t>(ix->n);
+  AB_CHECK(n > 64 && ix->n_raw == ix->n, AB_ERR_STATE, "fit the spaces first (at least 65 rows)");
+  const uint32_t L = std::max<uint32_t>(ef_construction, kR);
+  AB_CHECK(L <= 4096, AB_ERR_INVALID, "ef_construction larger than 4096 is not supported");
+  const bool ip = ix->params.metric != AB_METRIC_L2;
+  const size_t stride = size_t(ix->raw_stride) * 4;
+  NsgWorkspace W;
+  nndescent_build(ix, kR, 10, nnd_iters, W, ip, nullptr);
+  stage("nn-descent");
+
+  // reverse_kernel folds at most kMaxIncoming reverse edges into a row per batch: keep batches small relative to n
+  const uint32_t max_batch = std::min<uint32_t>(16384, std::max<uint32_t>(256, n / 64));
+  Workspace w;
+  w.pool_ids.reserve(size_t(max_batch) * L);
+  w.pool_dist.reserve(size_t(max_batch) * L);
+  w.pool_sizes.reserve(max_batch);
+  w.first.reserve(max_batch);
+  const uint32_t max_edges = max_batch * kR;
+  w.edge_dst.reserve(max_edges);
+  w.edge_src.reserve(max_edges);
+  w.edge_dist.reserve(max_edges);
+  w.sorted_dst.reserve(max_edges);
+  w.idx.reserve(max_edges);
+  w.sorted_idx.reserve(max_edges);
+  w.counter.reserve(1);
+  w.stats.reserve(8);
+  AB_CUDA(cudaMemsetAsync(w.stats.p, 0, 64, s));
+  iota_kernel<<<(max_edges + 255) / 256, 256, 0, s>>>(w.idx.p, max_edges);
+  AB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, w.edge_dst.p, w.sorted_dst.p, w.idx.p, w.sorted_idx.p,
+                                          static_cast<int>(max_edges), 0, 32, s));
+  w.cub_tmp.reserve(w.cub_bytes + 16);
+  DevBuf<uint32_t> cid_ws, d_iota;
+  DevBuf<float> cd_ws, centroid;
+  cid_ws.reserve(size_t(max_batch) * L);
+  cd_ws.reserve(size_t(max_batch) * L);
+  centroid.reserve(ix->raw_stride);
+  d_iota.reserve(n);
+  iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_iota.p, n);
+  AB_CUDA(cudaMemsetAsync(centroid.p, 0, ix->raw_stride * 4, s));
+  centroid_kernel<<<ix->dim, 256, 0, s>>>(ix->raw.p, n, ix->dim, ix->raw_stride, centroid.p);
+  AB_CUDA(cudaGetLastError());
+  count_launch(3);
+  stage("centroid");
+
+  // ---- init(): navigating node = best hit of a traversal of the k-NN graph for the centroid -------------------
+  LayerView view{reinterpret_cast<const uint8_t *>(ix->raw.p), stride, ix->raw_chunks, ix->adj.p, kR};
+  search_rows_on_graph(ix, view, W.knng.p, centroid.p, nullptr, ix->raw_stride, 1, L, nnd_hash(n, 0x1234u) % n, w, ip, s);
+  uint32_t ep = 0;
+  stage("navigating node search");
+  AB_CUDA(cudaMemcpyAsync(&ep, w.first.p, 4, cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+  AB_CHECK(ep < n, AB_ERR_STATE, "NSG: navigating node search failed");
+
+  // ---- link(): candidates from the k-NN graph, MRNG prune, reverse links, batch by batch --------------------
+  AB_CUDA(cudaMemsetAsync(ix->adj.p, 0xFF, ix->capacity * kR * 4, s));
+  const int tpv = pick_build_tpv(ix->raw_chunks);
+  const int warps = 4;
+  const size_t smem = build_warp_smem(ix->raw_chunks) * warps;
+  for (uint32_t done = 0; done < n; done += max_batch) {
+    const uint32_t B = std::min(max_batch, n - done);
+    const uint32_t *batch_ids = d_iota.p + done;
+    search_rows_on_graph(ix, view, W.knng.p, ix->raw.p, batch_ids, ix->raw_stride, B, L, ep, w, ip, s);
+    stage("link: search");
+    const int blocks = std::max(1, std::min<int>((B + warps - 1) / warps, ix->sm_count * 8));
+#define AB_NSEL(IPV, T)                                                                                    \
+  {                                                                                                        \
+    auto k = nsg_select_kernel<IPV, T>;                                                                    \
+    AB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+    k<<<blocks, warps * 32, smem, s>>>(view, batch_ids, B, w.pool_ids.p, w.pool_dist.p, w.pool_sizes.p, L, w.edge_dst.p, w.edge_src.p, \
+                                       w.edge_dist.p, cid_ws.p, cd_ws.p);                                  \
+  }
+#define AB_NSEL_T(IPV)                  \
+  switch (tpv) {                        \
+    case 4: AB_NSEL(IPV, 4); break;     \
+    case 8: AB_NSEL(IPV, 8); break;     \
+    case 16: AB_NSEL(IPV, 16); break;   \
+    default: AB_NSEL(IPV, 32); break;   \
+  }
+    if (ip) { AB_NSEL_T(true) } else { AB_NSEL_T(false) }
+#undef AB_NSEL_T
+#undef AB_NSEL
+    AB_CUDA(cudaGetLastError());
+    count_launch(2);
+    stage("link: prune");
+  }
+  // add_reverse_links (nsg_builder.hpp:438-520) once every row exists: the out-edges of a batch of nodes, grouped by
+  // target, appended to / re-pruned into the target rows (duplicates of existing links dropped)
+  for (uint32_t done = 0; done < n; done += max_batch) {
+    const uint32_t B = std::min(max_batch, n - done);
+    const uint32_t *batch_ids = d_iota.p + done;
+    const int blocks = std::max(1, std::min<int>((B + warps - 1) / warps, ix->sm_count * 8));
+    if (ip) nsg_edges_kernel<true><<<blocks, warps * 32, 0, s>>>(view, batch_ids, B, w.edge_dst.p, w.edge_src.p, w.edge_dist.p);
+    else nsg_edges_kernel<false><<<blocks, warps * 32, 0, s>>>(view, batch_ids, B, w.edge_dst.p, w.edge_src.p, w.edge_dist.p);
+    AB_CUDA(cudaGetLastError());
+    const uint32_t nedges = B * kR;
+    AB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, w.cub_bytes, w.edge_dst.p, w.sorted_dst.p, w.idx.p, w.sorted_idx.p,
+                                            static_cast<int>(nedges), 0, 32, s));
+    count_launch(3);
+    stage("reverse: sort");
+    if (ip) launch_reverse<true>(tpv, view, w, nedges, ix->sm_count, s, 1);
+    else launch_reverse<false>(tpv, view, w, nedges, ix->sm_count, s, 1);
+    stage("reverse: merge");
+  }
+
+  // ---- tree_grow(): every node reachable from the navigating node (host breadth-first pass) -------------------
+  std::vector<uint32_t> adj(size_t(n) * kR);
+  AB_CUDA(cudaMemcpyAsync(adj.data(), ix->adj.p, adj.size() * 4, cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+  std::vector<uint8_t> seen(n, 0);
+  std::vector<uint32_t> queue;
+  queue.reserve(n);
+  auto bfs_from = [&](uint32_t root) {
+    if (seen[root]) return;
+    seen[root] = 1;
+    size_t head = queue.size();
+    queue.push_back(root);
+    while (head < queue.size()) {
+      const uint32_t u = queue[head++];
+      for (int j = 0; j < kR; j++) {
+        const uint32_t v = adj[size_t(u) * kR + j];
+        if (v == kEmptyId) break;
+        if (v < n && !seen[v]) {
+          seen[v] = 1;
+          queue.push_back(v);
+        }
+      }
+    }
+  };
+  bfs_from(ep);
+  uint64_t attached = 0;
+  for (uint32_t x = 0; x < n; x++) {
+    if (seen[x]) continue;
+    // attach x below the nearest reached node of its own (distance-sorted) list; a full row gives up its last edge
+    uint32_t parent = kEmptyId;
+    for (int j = 0; j < kR && parent == kEmptyId; j++) {
+      const uint32_t y = adj[size_t(x) * kR + j];
+      if (y == kEmptyId) break;
+      if (y < n && seen[y]) parent = y;
+    }
+    if (parent == kEmptyId) parent = ep;
+    uint32_t *row = adj.data() + size_t(parent) * kR;
+    int deg = 0;
+    while (deg < kR && row[deg] != kEmptyId) deg++;
+    row[deg < kR ? deg : kR - 1] = x;
+    attached++;
+    bfs_from(x);
+  }
+  if (attached) AB_CUDA(cudaMemcpyAsync(ix->adj.p, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+
+  ix->ov_rows = 0;
+  ix->ep = ep;
+  ix->ep_level = 0;
+  ix->has_overlay = false;
+  ix->has_graph = true;
+  std::fill(ix->h_levels.begin(), ix->h_levels.begin() + n, 0);
   std::fill(ix->h_valid_graph.begin(), ix->h_valid_graph.begin() + n, 1);
 }
 

@@ -496,6 +496,26 @@ int ab_index_build_graph(ab_index *index, uint32_t ef_construction) {
   });
 }
 
+int ab_index_build_graph_nsg(ab_index *index, uint32_t ef_construction, uint32_t nndescent_iters) {
+  return guarded([&] {
+    AB_CHECK(index != nullptr && index->n > 0, AB_ERR_STATE, "fit the spaces first");
+    std::lock_guard<std::mutex> lock(index->mu);
+    use_device(index);
+    index_order_after_searches(index, index->stream);
+    index_build_graph_nsg(index, ef_construction, nndescent_iters == 0 ? 10 : nndescent_iters);
+  });
+}
+
+int ab_index_knng_nndescent(ab_index *index, uint32_t k, uint32_t iters, uint32_t *out_ids) {
+  return guarded([&] {
+    AB_CHECK(index != nullptr && index->n > 0 && out_ids != nullptr, AB_ERR_STATE, "fit the spaces first");
+    std::lock_guard<std::mutex> lock(index->mu);
+    use_device(index);
+    index_order_after_searches(index, index->stream);
+    index_knng_nndescent(index, k, iters == 0 ? 10 : iters, out_ids);
+  });
+}
+
 int ab_index_fit(ab_index *index, const float *data, uint64_t n, uint32_t dim, uint32_t ef_construction,
                  uint32_t num_threads) {
   (void)num_threads;

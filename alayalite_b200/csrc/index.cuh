@@ -99,6 +99,9 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
 void index_save(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_load(ab_index *ix, const char *index_path, const char *data_path, const char *quant_path);
 void index_build_graph(ab_index *ix, uint32_t ef_construction);
+// NN-Descent k-NN graph + NSG (build.cu)
+void index_build_graph_nsg(ab_index *ix, uint32_t ef_construction, uint32_t nnd_iters);
+void index_knng_nndescent(ab_index *ix, uint32_t K, uint32_t iters, uint32_t *out_ids);
 uint32_t index_insert(ab_index *ix, const float *vec, uint32_t ef);
 void index_remove(ab_index *ix, uint32_t id);
 void index_sync_valid_bitmap(ab_index *ix);

@@ -127,6 +127,16 @@ int ab_index_fit_spaces(ab_index *index, const float *data, uint64_t n, uint32_t
 int ab_index_set_graph(ab_index *index, const uint32_t *adj, const uint32_t *levels,
                        const uint32_t *lists_flat, uint64_t lists_len, uint32_t ep);
 int ab_index_build_graph(ab_index *index, uint32_t ef_construction);
+/* NSGBuilder::build_graph (include/index/graph/nsg/nsg_builder.hpp:97-161) on the device, after ab_index_fit_spaces:
+ * NN-Descent k-NN graph (include/index/graph/knng/nndescent.hpp:142-400; K = 32, S = 10, nndescent_iters iterations,
+ * 0 = the reference's 10) -> navigating node = nearest row to the centroid -> per node the candidates of a traversal
+ * of the k-NN graph at ef_construction pruned with the MRNG rule to <= 32 edges -> reverse links -> connectivity pass.
+ * The result is a flat graph (one entry point, no overlay) in the reference's Graph layout and file format. Only
+ * reachable from C++ in the reference (PyIndex::fit builds HNSW for every index type, and so does ab_index_fit). */
+int ab_index_build_graph_nsg(ab_index *index, uint32_t ef_construction, uint32_t nndescent_iters);
+/* NndescentImpl::build_graph alone: out_ids [n, 32], the k nearest neighbours found for every row in ascending
+ * distance, 0xFFFFFFFF beyond k (k <= 32). */
+int ab_index_knng_nndescent(ab_index *index, uint32_t k, uint32_t iters, uint32_t *out_ids);
 /* info = {n, R, ep, lists_len, capacity} */
 int ab_index_graph_info(ab_index *index, uint64_t info[5]);
 int ab_index_get_graph(ab_index *index, uint32_t *adj, uint32_t *levels, uint32_t *lists_flat);

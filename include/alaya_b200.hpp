@@ -236,6 +236,15 @@ class DeviceSearchJob {
     space_->index().batch_search_with_distance(query, 1, k, ef, tmp.data(), distances);
     for (uint32_t i = 0; i < k; i++) ids[i] = static_cast<IDType>(tmp[i]);
   }
+  // graph_search_job.hpp:373-417. The reference expands a removed vertex through the neighbour list saved at
+  // removal time; on the device a removed vertex's adjacency row is frozen at that very list (updates skip invalid
+  // rows like SequentialStorage::update does), so the ordinary traversal IS the updated one. Pool order, no re-rank.
+  void search_solo_updated(const DataType *query, uint32_t k, IDType *ids, uint32_t ef) {
+    std::vector<uint32_t> tmp(k);
+    std::vector<float> dist(k);
+    space_->index().batch_search_with_distance(query, 1, k, ef, tmp.data(), dist.data());
+    for (uint32_t i = 0; i < k; i++) ids[i] = static_cast<IDType>(tmp[i]);
+  }
   // PyIndex::batch_search (python/include/index.hpp:289-346) without the Python types
   void batch_search(const DataType *queries, uint64_t nq, uint32_t k, IDType *ids, uint32_t ef) {
     if constexpr (std::is_same<IDType, uint32_t>::value) {

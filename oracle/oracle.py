@@ -200,6 +200,22 @@ class CheckerIndex:
         self._check(self.chk.lib.orc_index_fit(self.h, _p(data, f32p), C.c_uint32(self.n), C.c_uint32(ef_construction), C.byref(calls)))
         return calls.value
 
+    def fit_nsg(self, data, ef_construction=100):
+        """The reference's NSGBuilder (NN-Descent + link + tree_grow); reference only."""
+        assert self.chk.which == "ref"
+        data = _f32(data)
+        self.n = data.shape[0]
+        self._data = data
+        self._check(self.chk.lib.ref_index_fit_nsg(self.h, _p(data, f32p), C.c_uint32(self.n), C.c_uint32(ef_construction)))
+
+    def knng(self, data, k=32):
+        """The reference's NndescentImpl k-NN graph: ids [n, k]; reference only."""
+        assert self.chk.which == "ref"
+        data = _f32(data)
+        out = np.zeros((data.shape[0], k), np.uint32)
+        self._check(self.chk.lib.ref_index_knng(self.h, _p(data, f32p), C.c_uint32(data.shape[0]), C.c_uint32(k), _p(out, u32p)))
+        return out
+
     def fit_spaces(self, data):
         assert self.chk.which == "orc"
         data = _f32(data)
@@ -262,6 +278,14 @@ class CheckerIndex:
         q = _f32(query).copy()
         ids = np.zeros(topk, np.uint32)
         self._check(self.chk._fn("index_search")(self.h, _p(q, f32p), C.c_uint32(topk), C.c_uint32(ef), _p(ids, u32p)))
+        return ids
+
+    def search_updated(self, query, topk, ef=100):
+        """GraphSearchJob::search_solo_updated (reference only): pool order, no re-rank."""
+        assert self.chk.which == "ref"
+        q = _f32(query).copy()
+        ids = np.zeros(topk, np.uint32)
+        self._check(self.chk.lib.ref_index_search_updated(self.h, _p(q, f32p), C.c_uint32(topk), C.c_uint32(ef), _p(ids, u32p)))
         return ids
 
     def batch_search(self, queries, topk, ef=100, num_threads=1, solo=False):

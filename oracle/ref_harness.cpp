@@ -24,6 +24,8 @@
 #include "executor/jobs/graph_update_job.hpp"
 #include "executor/scheduler.hpp"
 #include "index/graph/hnsw/hnsw_builder.hpp"
+#include "index/graph/knng/nndescent.hpp"
+#include "index/graph/nsg/nsg_builder.hpp"
 #include "simd/cpu_features.hpp"
 #include "simd/distance_ip.hpp"
 #include "simd/distance_l2.hpp"
@@ -41,7 +43,10 @@ thread_local std::string g_err;
 struct RefIndexBase {
   virtual ~RefIndexBase() = default;
   virtual void fit(float *data, uint32_t n, uint32_t efc, uint32_t threads) = 0;
+  virtual void fit_nsg(float *data, uint32_t n, uint32_t efc) = 0;
+  virtual void knng(float *data, uint32_t n, uint32_t k, uint32_t *out) = 0;
   virtual void search(float *q, uint32_t topk, uint32_t ef, uint32_t *ids) = 0;
+  virtual void search_updated(float *q, uint32_t topk, uint32_t ef, uint32_t *ids) = 0;
   virtual void batch_search(float *q, uint32_t nq, uint32_t topk, uint32_t ef, uint32_t threads,
                             uint32_t *ids) = 0;
   virtual void batch_search_solo(float *q, uint32_t nq, uint32_t topk, uint32_t ef,
@@ -100,6 +105,30 @@ struct RefIndex : RefIndexBase {
     make_jobs();
   }
 
+  // NSGBuilder::build_graph (include/index/graph/nsg/nsg_builder.hpp:97-161): NN-Descent + link + tree_grow
+  void fit_nsg(float *data, uint32_t n, uint32_t efc) override {
+    build_space_ = std::make_shared<BuildSpace>(capacity_, dim_, metric_);
+    build_space_->fit(data, n);
+    if constexpr (kSame) {
+      search_space_ = build_space_;
+    } else {
+      search_space_ = std::make_shared<SearchSpace>(capacity_, dim_, metric_);
+      search_space_->fit(data, n);
+    }
+    auto builder = std::make_shared<NSGBuilder<BuildSpace>>(build_space_, max_nbrs_, efc);
+    graph_ = builder->build_graph();
+    make_jobs();
+  }
+  // NndescentImpl::build_graph (include/index/graph/knng/nndescent.hpp:142-176): ids [n, k]
+  void knng(float *data, uint32_t n, uint32_t k, uint32_t *out) override {
+    auto sp = std::make_shared<BuildSpace>(capacity_, dim_, metric_);
+    sp->fit(data, n);
+    NndescentImpl<BuildSpace> nnd(sp, k);
+    auto g = nnd.build_graph();
+    for (uint32_t i = 0; i < n; i++)
+      for (uint32_t j = 0; j < k; j++) out[size_t(i) * k + j] = g->at(i, j);
+  }
+
   template <typename QC>
   static void rerank(std::vector<uint32_t> &src, uint32_t *dst, float *dist, QC qc, uint32_t ef,
                      uint32_t topk) {
@@ -122,6 +151,12 @@ struct RefIndex : RefIndexBase {
     } else {
       rerank(res_pool, ids, nullptr, build_space_->get_query_computer(q), ef, topk);
     }
+  }
+
+  // GraphSearchJob::search_solo_updated (graph_search_job.hpp:373-417): the search that consults the update
+  // context (removed vertices expand through their saved neighbour lists); search-space order, no re-rank
+  void search_updated(float *q, uint32_t topk, uint32_t ef, uint32_t *ids) override {
+    search_job_->search_solo_updated(q, topk, ids, ef);
   }
 
   void finish(std::vector<std::vector<uint32_t>> &res_pool, float *q, uint32_t nq, uint32_t topk,
@@ -343,8 +378,17 @@ void ref_index_destroy(void *h) { delete static_cast<RefIndexBase *>(h); }
 int ref_index_fit(void *h, float *data, uint32_t n, uint32_t efc, uint32_t threads) {
   return guarded([&] { static_cast<RefIndexBase *>(h)->fit(data, n, efc, threads); });
 }
+int ref_index_fit_nsg(void *h, float *data, uint32_t n, uint32_t efc) {
+  return guarded([&] { static_cast<RefIndexBase *>(h)->fit_nsg(data, n, efc); });
+}
+int ref_index_knng(void *h, float *data, uint32_t n, uint32_t k, uint32_t *out) {
+  return guarded([&] { static_cast<RefIndexBase *>(h)->knng(data, n, k, out); });
+}
 int ref_index_search(void *h, float *q, uint32_t topk, uint32_t ef, uint32_t *ids) {
   return guarded([&] { static_cast<RefIndexBase *>(h)->search(q, topk, ef, ids); });
+}
+int ref_index_search_updated(void *h, float *q, uint32_t topk, uint32_t ef, uint32_t *ids) {
+  return guarded([&] { static_cast<RefIndexBase *>(h)->search_updated(q, topk, ef, ids); });
 }
 int ref_index_batch_search(void *h, float *q, uint32_t nq, uint32_t topk, uint32_t ef,
                            uint32_t threads, uint32_t *ids) {

@@ -66,6 +66,38 @@ def test_insert_remove_match_reference(cabi, metric, quant):
             ix.get_data_by_id(600)  # the raw space was not extended (graph_update_job.hpp:75)
 
 
+@pytest.mark.parametrize("quant", ["none", "sq8"])
+def test_search_after_removes_equals_reference_search_solo_updated(cabi, ref, quant):
+    """GraphSearchJob::search_solo_updated (graph_search_job.hpp:373-417) walks removed vertices through the neighbour
+    lists saved at removal time. The device keeps a removed vertex's adjacency row frozen at exactly that list, so the
+    ordinary traversal must return the reference's ids, step for step."""
+    from alayalite_b200.synthetic import integer_grid, low_rank
+    if quant == "none":
+        base, q = integer_grid(1500, 24, 60, seed=3, hi=10)  # integer coordinates: every fp32 sum exact, ties included
+    else:  # code-space sums are not exact: a grid would turn its many exact ties into coin flips
+        base, q = low_rank(1500, 24, 60, latent=6, seed=3)
+    r = ref.index("l2", quant, 1600, 24)
+    r.fit(base.copy(), 40, 1)
+    g = r.graph()
+    ix = cabi.NativeIndex("l2", quant, 1600)
+    ix.fit_spaces(base)
+    ix.set_graph(g["adj"], g["levels"], g["lists_flat"], g["ep"])
+    # remove hubs that the traversals certainly cross: the most frequent level-0 neighbours
+    adj = g["adj"][:1500]
+    hubs = np.argsort(-np.bincount(adj[adj != 0xFFFFFFFF], minlength=1500))[:12]
+    for v in hubs.tolist():
+        r.remove(v)
+        ix.remove(v)
+    for ef, k in ((32, 10), (64, 32)):
+        got, _ = ix.batch_search_with_distance(q, k, ef)  # pool order, no re-rank
+        want = np.stack([r.search_updated(q[i], k, ef) for i in range(len(q))])
+        if quant == "none":
+            assert np.array_equal(got, want), (quant, ef, k)  # integer coordinates: exact, ties included
+        else:  # code-space distances are not exact sums: identical up to fp32 summation-order ties
+            assert np.mean(np.all(got == want, axis=1)) >= 0.9, (quant, ef, k)
+            assert np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(got, want)]) >= 0.98
+
+
 def test_insert_until_full_and_sdk_errors(cabi):
     from alayalite_b200 import Client
 
