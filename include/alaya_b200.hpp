@@ -197,6 +197,43 @@ class DeviceGraphBuilder {
   uint32_t ef_construction_;
 };
 
+// NSGBuilder's shape (include/index/graph/nsg/nsg_builder.hpp:60-161): NN-Descent k-NN graph + MRNG link + reverse
+// links + connectivity pass on the device (ab_index_build_graph_nsg). The result is the reference's own Graph with
+// eps_ = {navigating node} and no overlay, and it stays resident in the space's index for DeviceSearchJob.
+template <class SpaceT, class GraphT>
+class DeviceNSGBuilder {
+ public:
+  using DistanceSpaceTypeAlias = SpaceT;
+  explicit DeviceNSGBuilder(std::shared_ptr<SpaceT> space, uint32_t max_nbrs = 32, uint32_t ef_construction = 200)
+      : space_(std::move(space)), ef_construction_(ef_construction) {
+    if (max_nbrs != 32) throw std::runtime_error("DeviceNSGBuilder: max_nbrs must be 32");
+  }
+  uint32_t nndescent_iters_ = 10;  // NSGBuilder::nndescent_iters_
+
+  auto build_graph(uint32_t /*thread_num*/ = 1) -> std::unique_ptr<GraphT> {
+    auto &ix = space_->index();
+    check(ab_index_build_graph_nsg(ix.get(), ef_construction_, nndescent_iters_));
+    uint64_t info[5];
+    check(ab_index_graph_info(ix.get(), info));
+    const uint64_t n = info[0], R = info[1];
+    std::vector<uint32_t> adj(n * R), levels(n), lists(1);
+    check(ab_index_get_graph(ix.get(), adj.data(), levels.data(), lists.data()));
+    using Node = std::remove_reference_t<decltype(std::declval<GraphT &>().at(0, 0))>;
+    auto g = std::make_unique<GraphT>(static_cast<Node>(space_->get_capacity()), static_cast<uint32_t>(R));
+    std::vector<Node> row(R);
+    for (uint64_t i = 0; i < n; i++) {
+      for (uint64_t j = 0; j < R; j++) row[j] = static_cast<Node>(adj[i * R + j]);
+      g->insert(row.data());
+    }
+    g->eps_.push_back(static_cast<Node>(info[2]));  // nsg_builder.hpp:113
+    return g;
+  }
+
+ private:
+  std::shared_ptr<SpaceT> space_;
+  uint32_t ef_construction_;
+};
+
 // Search over the graph resident in the space's index (replaces GraphSearchJob,
 // include/executor/jobs/graph_search_job.hpp). The coroutine / Scheduler machinery has no counterpart:
 // batch_search is one kernel launch over all queries.

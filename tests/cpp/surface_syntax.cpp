@@ -5,6 +5,7 @@
 using Space = alaya_b200::DeviceSpace<>;
 template class alaya_b200::DeviceSpace<float, float, uint32_t>;
 template class alaya_b200::DeviceGraphBuilder<Space, MockGraph>;
+template class alaya_b200::DeviceNSGBuilder<Space, MockGraph>;
 template class alaya_b200::DeviceSearchJob<Space>;
 template void alaya_b200::DeviceSearchJob<Space>::set_graph<MockGraph>(const MockGraph &);
 
