@@ -199,7 +199,8 @@ void index_search_device(ab_index *ix, const float *d_queries, uint64_t nq, uint
   AB_CHECK(topk >= 1 && ef >= 1, AB_ERR_INVALID, "topk and ef must be positive");
   // the reference reads uninitialised pool slots when topk > ef (SURVEY.md 8b "Errors"); rejected here
   AB_CHECK(topk <= ef, AB_ERR_INVALID, "topk must not exceed ef");
-  AB_CHECK(ef <= 4096, AB_ERR_INVALID, "ef larger than 4096 is not supported");
+  // the pool of one query lives in shared memory (8 bytes per entry): that, not the visited set, bounds ef
+  AB_CHECK(ef <= 24576, AB_ERR_INVALID, "ef larger than 24576 is not supported (the candidate pool must fit one SM's shared memory)");
   if (nq == 0) return;
   // the workspace below is shared by every launch on this handle: order this one behind the previous user
   index_order_after_searches(ix, stream);

@@ -327,6 +327,9 @@ static SearchPlan plan_search_impl(int quant, int nchunks, int table_len, float 
   uint32_t o = ovf_forced ? 64u : 4096u;
   while (o < want) o <<= 1;
   p.ovf_size = o;
+  // (the sticky all-warps sizing is for the common small tables only: at a very large ef few warps are resident and
+  // their tables are megabytes each)
+  if (o > 16384) p.max_slots = p.slots;
   return p;
 }
 

@@ -76,7 +76,7 @@ int ab_index_fit(ab_index *index, const float *data, uint64_t n, uint32_t dim,
 /* PyIndex::search (index.hpp:236-258): one query, ids[topk]. */
 int ab_index_search(ab_index *index, const float *query, uint32_t topk, uint32_t ef, uint32_t *out_ids);
 
-/* PyIndex::batch_search (index.hpp:289-346): queries [nq, dim] -> ids [nq, topk]. SQ spaces are
+/* PyIndex::batch_search (index.hpp:289-346): queries [nq, dim] -> ids [nq, topk] (topk <= ef <= 24576). SQ spaces are
  * re-ranked with exact raw-space distances exactly like index.hpp:337-345 / :450-467. */
 int ab_index_batch_search(ab_index *index, const float *queries, uint64_t nq, uint32_t topk,
                           uint32_t ef, uint32_t num_threads, uint32_t *out_ids);

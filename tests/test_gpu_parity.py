@@ -307,6 +307,18 @@ def test_small_index_and_ef_edge_cases(cabi, orc):
     assert ix.batch_search(q[:0], 3, 10).shape == (0, 3)
 
 
+def test_very_large_ef_is_exact(cabi, orc, small_sets):
+    """ef far above the round-1 limit of 4096 (the reference has none): one warp per CTA, the pool alone takes 64 KB of
+    shared memory, the visited set runs through all three levels; ids must still equal the oracle's."""
+    base, q = small_sets["grid"]
+    o, ix = _pair(cabi, orc, base, "l2", "none")
+    want = o.batch_search(q[:20], 50, 8192)
+    got = ix.batch_search(q[:20], 50, 8192)
+    assert np.array_equal(got, want)
+    with pytest.raises(RuntimeError):
+        ix.batch_search(q[:2], 10, 30000)
+
+
 def test_visited_spill_to_bitmap_is_exact(cabi, orc, small_sets):
     """Large ef overflows the shared-memory hash; the global-bitmap continuation must stay exact."""
     base, q = small_sets["grid"]
