@@ -518,7 +518,7 @@ static void tc_run(int metric, const float *d_rows, uint64_t n, uint32_t dim, ui
   AB_CHECK(n >= k && k <= 256, AB_ERR_INVALID, "bruteforce_topk_tc: needs k <= min(n, 256)");
   // ---- pass A: exact top-k over a sample (a prefix of the rows) -> tau ------------------------------
   const uint64_t sample = level == 0 ? std::min<uint64_t>(n, std::max<uint64_t>(16384, n / 32))
-                                     : std::min<uint64_t>(n, std::max<uint64_t>(std::max<uint64_t>(2048, 4ull * k), n / 8));
+                                     : std::min<uint64_t>(n, std::max<uint64_t>(std::max<uint64_t>(2048, 4ull * k), n / 16));
   // grow-only workspace kept per (device, level): cudaMalloc / cudaFree around every call cost ~4 ms of the 16
   // (serialised by the lock taken in bruteforce_topk_tc)
   static TcWorkspace ws_all[16][2];

@@ -438,7 +438,10 @@ void index_build_graph(ab_index *ix, uint32_t ef_construction) {
   // ---- workspace ---------------------------------------------------------------------------------
   // batch schedule: a batch never exceeds 1/growth_div of what is already inserted (new points of one
   // batch do not see each other) nor max_batch. Tunable for experiments through the environment.
-  uint32_t max_batch = 2048, growth_div = 64;
+  // The cap also follows n: the points of one batch are inserted blind to each other, which costs recall at small ef
+  // once a batch is more than ~0.25 % of the set (200k x 128, ef 16: -0.004 at 2048 per batch, -0.0001 at 512;
+  // profiles/build_quality_r01.txt). From 820k rows on the cap is 2048.
+  uint32_t max_batch = std::min<uint32_t>(2048, std::max<uint32_t>(64, n / 400)), growth_div = 64;
   if (const char *e = std::getenv("AB_BUILD_MAXB")) max_batch = std::max(1, std::atoi(e));
   if (const char *e = std::getenv("AB_BUILD_DIV")) growth_div = std::max(1, std::atoi(e));
   Workspace w;
