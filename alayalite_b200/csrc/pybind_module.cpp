@@ -11,7 +11,9 @@
 #include <pybind11/stl.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -67,9 +69,34 @@ class PyIndexInterface {
     p.capacity = params.capacity_;
     p.max_nbrs = params.max_nbrs_;
     p.device = -1;
+    // Several GPUs without touching the reference's Python API: ALAYA_B200_DEVICES="0,1,2,3" (CUDA ordinals) and
+    // optionally ALAYA_B200_SHARDS=S (default 1: every GPU holds a replica and the query batch is split; S > 1: the
+    // rows are split by contiguous id ranges over S GPUs and the lists are merged in the search kernel). The index
+    // then lives in an ab_group (include/alaya_b200.h, "Multi-GPU"); fit / batch_search work as usual, the
+    // single-vector and persistence calls are refused.
+    if (const char *devs = std::getenv("ALAYA_B200_DEVICES")) {
+      std::vector<int32_t> ids;
+      std::stringstream ss(devs);
+      for (std::string tok; std::getline(ss, tok, ',');)
+        if (!tok.empty()) ids.push_back(std::stoi(tok));
+      const char *sh = std::getenv("ALAYA_B200_SHARDS");
+      const uint32_t shards = sh ? static_cast<uint32_t>(std::max(1, std::atoi(sh))) : 1u;
+      if (ids.size() > 1) {
+        if (ids.size() % shards != 0) throw std::runtime_error("ALAYA_B200_DEVICES must hold a multiple of ALAYA_B200_SHARDS devices");
+        ab_group *g = nullptr;
+        check(ab_group_create(&p, ids.data(), shards, static_cast<uint32_t>(ids.size() / shards), &g));
+        group_.reset(g, ab_group_destroy);
+        return;
+      }
+      if (ids.size() == 1) p.device = ids[0];
+    }
     ab_index *h = nullptr;
     check(ab_index_create(&p, &h));
     handle_.reset(h, ab_index_destroy);
+  }
+
+  void single_gpu_only(const char *what) const {
+    if (group_) throw std::runtime_error(std::string(what) + " is not available on a multi-GPU index (ALAYA_B200_DEVICES)");
   }
 
   auto to_string() -> std::string { return "PyIndexInterface"; }
@@ -83,7 +110,8 @@ class PyIndexInterface {
     const auto d = static_cast<uint32_t>(v.shape(1));
     {
       py::gil_scoped_release nogil;
-      check(ab_index_fit(handle_.get(), ptr, n, d, ef_construction, num_threads));
+      if (group_) check(ab_group_fit(group_.get(), ptr, n, d, ef_construction));
+      else check(ab_index_fit(handle_.get(), ptr, n, d, ef_construction, num_threads));
     }
     data_dim_ = d;
   }
@@ -92,11 +120,13 @@ class PyIndexInterface {
     FloatArray q = FloatArray::ensure(query);
     if (!q) throw std::runtime_error("Unsupported data type");
     py::array_t<uint32_t> ids(static_cast<py::ssize_t>(topk));
-    check(ab_index_search(handle_.get(), q.data(), topk, ef, ids.mutable_data()));
+    if (group_) check(ab_group_batch_search(group_.get(), q.data(), 1, topk, ef, ids.mutable_data(), nullptr));
+    else check(ab_index_search(handle_.get(), q.data(), topk, ef, ids.mutable_data()));
     return cast_ids(ids);
   }
 
   auto get_data_by_id(uint32_t id) -> py::array {
+    single_gpu_only("get_data_by_id");
     const uint32_t d = ab_index_get_dim(handle_.get());
     py::array_t<float> out(static_cast<py::ssize_t>(d));
     check(ab_index_get_data_by_id(handle_.get(), id, out.mutable_data()));
@@ -105,6 +135,7 @@ class PyIndexInterface {
   }
 
   auto insert(py::array &insert_data, uint32_t ef) -> py::object {
+    single_gpu_only("insert");
     FloatArray v = FloatArray::ensure(insert_data);
     if (!v) throw std::runtime_error("Unsupported data type");
     uint32_t id = 0;
@@ -113,7 +144,10 @@ class PyIndexInterface {
     return py::int_(id);
   }
 
-  void remove(uint32_t id) { check(ab_index_remove(handle_.get(), id)); }
+  void remove(uint32_t id) {
+    single_gpu_only("remove");
+    check(ab_index_remove(handle_.get(), id));
+  }
 
   auto batch_search(py::array &queries, uint32_t topk, uint32_t ef, uint32_t num_threads) -> py::array {
     FloatArray q = FloatArray::ensure(queries);
@@ -124,7 +158,8 @@ class PyIndexInterface {
     uint32_t *ip = ids.mutable_data();
     {
       py::gil_scoped_release nogil;
-      check(ab_index_batch_search(handle_.get(), qp, nq, topk, ef, num_threads, ip));
+      if (group_) check(ab_group_batch_search(group_.get(), qp, nq, topk, ef, ip, nullptr));
+      else check(ab_index_batch_search(handle_.get(), qp, nq, topk, ef, num_threads, ip));
     }
     return cast_ids(ids);
   }
@@ -136,24 +171,35 @@ class PyIndexInterface {
     py::array_t<uint32_t> ids(std::vector<py::ssize_t>{nq, static_cast<py::ssize_t>(topk)});
     py::array_t<float> dist(std::vector<py::ssize_t>{nq, static_cast<py::ssize_t>(topk)});
     int32_t has = 0;
-    check(ab_index_batch_search_with_distance(handle_.get(), q.data(), static_cast<uint64_t>(nq), topk, ef, num_threads,
-                                              ids.mutable_data(), dist.mutable_data(), &has));
+    if (group_) {
+      // the merged lists of a group are the re-ranked ones and always carry their exact distances
+      check(ab_group_batch_search(group_.get(), q.data(), static_cast<uint64_t>(nq), topk, ef, ids.mutable_data(), dist.mutable_data()));
+      has = 1;
+    } else {
+      check(ab_index_batch_search_with_distance(handle_.get(), q.data(), static_cast<uint64_t>(nq), topk, ef, num_threads,
+                                                ids.mutable_data(), dist.mutable_data(), &has));
+    }
     // index.hpp:416-418: for SQ spaces dist_pool stays empty -> a (0, topk) array
     if (!has) dist = py::array_t<float>(std::vector<py::ssize_t>{0, static_cast<py::ssize_t>(topk)});
     return py::make_tuple(cast_ids(ids), dist);
   }
 
   void save(const std::string &index_path, const std::string &data_path, const std::string &quant_path) {
+    single_gpu_only("save");
     check(ab_index_save(handle_.get(), index_path.c_str(), data_path.c_str(), quant_path.c_str()));
   }
   void load(const std::string &index_path, const std::string &data_path, const std::string &quant_path) {
+    single_gpu_only("load");
     check(ab_index_load(handle_.get(), index_path.c_str(), data_path.c_str(), quant_path.c_str()));
     data_dim_ = ab_index_get_dim(handle_.get());
   }
   auto get_data_dim() -> uint32_t { return data_dim_; }
 
   // not part of the reference surface: raw handle for the ctypes-level tools (bench, sharding)
-  auto handle() -> uintptr_t { return reinterpret_cast<uintptr_t>(handle_.get()); }
+  auto handle() -> uintptr_t {
+    single_gpu_only("_handle");
+    return reinterpret_cast<uintptr_t>(handle_.get());
+  }
 
   IndexParams params_;
 
@@ -163,6 +209,7 @@ class PyIndexInterface {
     return std::move(ids);
   }
   std::shared_ptr<ab_index> handle_;
+  std::shared_ptr<ab_group> group_;  // set instead of handle_ when ALAYA_B200_DEVICES names several GPUs
   uint32_t data_dim_{0};
 };
 

@@ -25,8 +25,8 @@ N > 1      One process per GPU (torchrun). Layout = shards x replicas (--layout 
            holds the whole index split by contiguous id ranges over S GPUs (peer-store exchange fused into the search
            kernel, merge by the last shard to arrive), and the R groups answer different query batches. `value` is
            ALWAYS end-user queries per second -- every query counted once, whatever the number of shards.
-           Extra blocks: `sharded` (the same 10M set split over N shards, strong scaling) and, at N = 8, `c5`
-           (100M x 96 over 8 shards).
+           Extra blocks: `sharded` (the same 10M set split over N shards, strong scaling) and `c5`
+           (100M x 96 split over the N shards).
 """
 
 from __future__ import annotations
@@ -84,6 +84,20 @@ def load_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1656.1)), "measured (MEASURED_PEAKS.json: hbm_gbs burst copy, bf16_tflops burst)"
     return 6650.0, 1650.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1.65 PF/s bf16)"
+
+
+def load_traffic(name, cfg, ef):
+    """DRAM bytes per launch of the traversal kernel from the committed `ncu --set full` capture of THIS workload at
+    THIS ef (profiles/traffic_r02.json, written by scripts/summarise_profiles.sh); anything else -> None."""
+    p = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(name)
+    if e and e.get("n") == cfg["n"] and e.get("dim") == cfg["dim"] and e.get("ef") == ef and e.get("nq") == cfg["nq"]:
+        return e["dram_bytes_read"] + e["dram_bytes_write"]
+    return None
 
 
 class ClockSampler:
@@ -330,7 +344,8 @@ def run_block(name, cfg, args, torch, dev, local_rank, stream, peaks, cpu=True, 
         "e2e": {"value": e2e_numpy, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 4,
                 "api": "alayalite_b200.Index.batch_search(numpy) -> pybind -> ab_index_batch_search (pageable host buffers)",
                 "recall": e2e_recall, "pinned": e2e_pinned, "pinned_api": "ab_index_batch_search on pinned host buffers (read / written in place by the kernels)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": load_traffic(name, cfg, ef),
+                     "traffic_source": "ncu --set full capture of this workload at this ef (profiles/ncu_search_r02.txt); null when the run's operating point differs",
                      "kernel": "beam_search_kernel" + (" + rerank_kernel" if cfg["quant"] != "none" else ""), "kernel_ms": ms,
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                      "per_query": {"ndc_level0": stats["ndc"] / nq, "ndc_overlay": stats["overlay"] / nq, "hops": stats["hops"] / nq, "bytes": alg / nq,

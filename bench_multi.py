@@ -9,7 +9,7 @@ main line   the north-star 10M x 128 index in the layout --layout SxR (default 1
             are fixed). Every shard answers every query; the exchange is fused into the search kernel (peer stores +
             last-arriver merge). Reports the step, the search alone and the exchange share, and asserts in the run that
             fused == NCCL all-gather + merge kernel == exact merge of the per-shard lists.
-`c5`        (N >= 4) BASELINE configs[4]: 100M x 96 split over the N shards, same measurements.
+`c5`        BASELINE configs[4]: 100M x 96 split over the N shards (50M rows per GPU at N = 2), same measurements.
 """
 
 from __future__ import annotations
@@ -218,7 +218,7 @@ def ours_multi(args, rank, world, local_rank):
     layouts = {(S, R)}
     blocks = [b for b in args.blocks.split(",") if b]
     want_sharded = (S, R) != (world, 1) and "nosharded" not in blocks
-    want_c5 = world >= 4 and "noc5" not in blocks
+    want_c5 = world >= 2 and "noc5" not in blocks
     if want_sharded or want_c5:
         layouts.add((world, 1))
     # process groups of every layout (new_group is collective: all ranks create all groups in the same order)

@@ -10,14 +10,23 @@ ap.add_argument("--n", type=int, default=1_000_000); ap.add_argument("--dim", ty
 ap.add_argument("--quant", default="none"); ap.add_argument("--metric", default="l2")
 ap.add_argument("--latent", type=int, default=16); ap.add_argument("--topk", type=int, default=10)
 ap.add_argument("--nq", type=int, default=10_000)
+ap.add_argument("--device-gen", action="store_true", help="generate rows on the GPU (bench.py's generator)")
 ap.add_argument("efs", nargs="*", type=int)
 a = ap.parse_args()
 efs = a.efs or [20, 52, 100]
 n, dim, nq, k = a.n, a.dim, a.nq, a.topk
-base, q = low_rank(n, dim, nq, a.latent, seed=42, normalize=(a.metric != "l2"))
 ix = _cabi.NativeIndex(a.metric, a.quant, n)
-t = time.time(); ix.fit(base, 100); print(f"fit {time.time()-t:.2f}s", flush=True)
-gt, _ = _cabi.bruteforce_topk("l2" if a.metric == "l2" else "ip", base, q, k)
+if a.device_gen:
+    from alayalite_b200.synthetic import low_rank_device
+    d_base, d_qq = low_rank_device(n, dim, nq, a.latent, seed=42, normalize=(a.metric != "l2"), device="cuda")
+    t = time.time(); ix.fit_ptr(d_base.data_ptr(), n, dim, 100); print(f"fit {time.time()-t:.2f}s", flush=True)
+    g_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda"); g_d = torch.empty((nq, k), device="cuda")
+    _cabi.bruteforce_topk_device("l2" if a.metric == "l2" else "ip", d_base.data_ptr(), n, dim, d_qq.data_ptr(), nq, k, g_ids.data_ptr(), g_d.data_ptr(), None)
+    torch.cuda.synchronize(); gt = g_ids.cpu().numpy().astype(np.uint32); q = d_qq.cpu().numpy(); del d_base
+else:
+    base, q = low_rank(n, dim, nq, a.latent, seed=42, normalize=(a.metric != "l2"))
+    t = time.time(); ix.fit(base, 100); print(f"fit {time.time()-t:.2f}s", flush=True)
+    gt, _ = _cabi.bruteforce_topk("l2" if a.metric == "l2" else "ip", base, q, k)
 row = {"none": dim * 4, "sq8": dim, "sq4": (dim + 1) // 2}[a.quant]
 stream = torch.cuda.Stream()
 d_q = torch.from_numpy(q).cuda(); d_ids = torch.zeros((nq, k), dtype=torch.int32, device="cuda"); d_dist = torch.zeros((nq, k), device="cuda")

@@ -28,4 +28,22 @@ for i, n in enumerate(h):
 PY
   echo >> $out
 done
+# DRAM bytes of the headline launch for bench.py's roofline.traffic (only used when the run's n / ef match)
+python - <<'PY'
+import csv, json, subprocess, os
+rep = "gpurun_out/prof_r02_raw10m.ncu-rep"
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, u, r = rows[0], rows[1], rows[-1]
+    def val(name):
+        i = h.index(name)
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u[i]]
+        return int(float(r[i]) * scale)
+    plain = json.load(open("gpurun_out/r02_prof_bench_plain.json"))
+    out = {"main": {"n": 10_000_000, "dim": 128, "nq": 10_000, "ef": plain["config"]["ef"], "dram_bytes_read": val("dram__bytes_read.sum"),
+                    "dram_bytes_write": val("dram__bytes_write.sum"), "source": "ncu --set full, one timed launch of python bench.py (profiles/ncu_search_r02.txt)"}}
+    json.dump(out, open("profiles/traffic_r02.json", "w"), indent=1)
+    print(out)
+PY
 wc -l $out

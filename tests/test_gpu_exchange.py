@@ -152,3 +152,38 @@ def test_comm_owner_rows_one_process_two_ranks(cabi, small_sets):
     assert all(c.errors() == 0 for c in comms)
     for c in comms:
         c.close()
+
+
+@pytest.mark.parametrize("shards", [1, 2])
+def test_sdk_runs_on_several_gpus_through_the_environment(shards, tmp_path):
+    """The reference's Python API, unchanged, on a multi-GPU index: ALAYA_B200_DEVICES (+ ALAYA_B200_SHARDS) makes the
+    pybind shell hold an ab_group. Run in a subprocess (the variables are read when the index is created); the two
+    'GPUs' are both device 0 on the single-GPU test box."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from alayalite_b200 import Client, calc_gt, calc_recall
+from alayalite_b200.synthetic import low_rank
+base, q = low_rank(6000, 32, 101, latent=8, seed=4)
+index = Client().create_index("multi", metric="l2", capacity=6000)
+index.fit(base, ef_construction=60)
+ids = index.batch_search(q, 10, ef_search=64)
+one = index.search(q[0], 10, 64)
+gt = calc_gt(base, q, 10)
+assert ids.shape == (101, 10) and np.array_equal(one, ids[0])
+assert calc_recall(ids, gt) > 0.97, calc_recall(ids, gt)
+ids2, dist = index.batch_search_with_distance(q, 10, 64)
+assert np.array_equal(ids2, ids) and dist.shape == (101, 10) and np.all(np.diff(dist, axis=1) >= 0)
+try:
+    index.insert(q[0])
+    raise SystemExit("insert must be refused on a multi-GPU index")
+except RuntimeError as e:
+    assert "multi-GPU" in str(e)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ALAYA_B200_DEVICES="0,0", ALAYA_B200_SHARDS=str(shards))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
