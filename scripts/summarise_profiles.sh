@@ -4,6 +4,7 @@ out=profiles/ncu_search_r02.txt
 : > $out
 for pair in "prof_r02_raw10m|beam_search_kernel, raw rows, 10M x 128 fp32 L2, 10k queries at the bench operating point (python bench.py, one timed step)" \
             "prof_r02_ef280|beam_search_kernel, raw rows, hard variant (L=32) 1M x 128, ef 280 (its 0.95 point), BEFORE double hashing / destination-tile merge" \
+            "prof_r02_ef280_final|beam_search_kernel, the same launch AFTER the round-2 changes (double hashing, destination-tile merge, six rows in flight)" \
             "prof_r02_c5_ef144|beam_search_kernel, one C5 shard: 12.5M x 96 fp32 L2, ef 144" \
             "prof_r02_sq8_c3|beam_search_kernel, SQ8 codes, C3 1M x 960 L2, ef 180" \
             "prof_r02_sq4_c4|beam_search_kernel, SQ4 codes, C4 shape 2M x 768 inner product, top-100, ef 160"; do
