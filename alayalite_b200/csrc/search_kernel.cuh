@@ -178,14 +178,15 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
     // (a failed CAS -- the slot or its neighbour half changed meanwhile -- re-reads the same slot).
     while (__any_sync(kFull, pending)) {
       if (pending) {
-        const uint32_t sh = (slot & 1u) << 4;
-        const uint32_t w = vs.hash[slot >> 1];
-        const uint32_t cur = (w >> sh) & 0xFFFFu;
+        const uint32_t cur = reinterpret_cast<const volatile uint16_t *>(vs.hash)[slot];  // one 16-bit shared load
         bool advance = true;
         if (cur == 0xFFFFu) {
           if (!vs.spilled) {
             advance = false;
-            if (atomicCAS(&vs.hash[slot >> 1], w, w ^ ((0xFFFFu ^ code) << sh)) == w) {
+            const uint32_t sh = (slot & 1u) << 4;
+            const uint32_t w = vs.hash[slot >> 1];
+            // (the half may have been claimed since the 16-bit read: then the same slot is simply probed again)
+            if (((w >> sh) & 0xFFFFu) == 0xFFFFu && atomicCAS(&vs.hash[slot >> 1], w, w ^ ((0xFFFFu ^ code) << sh)) == w) {
               is_new = true;
               pending = false;
             }
