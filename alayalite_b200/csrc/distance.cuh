@@ -474,19 +474,33 @@ __device__ __forceinline__ float sq_distance_multi(const uint8_t *r0, const uint
         }
         st += (NP / 2) * nchunks;
         mt += (NP / 2) * nchunks;
-        word_pairs<QUANT>(q.x, Q);
+        // SQ8 L2: |cq - cc| of four codes in ONE instruction (VABSDIFF4 is native on sm_100a), and the 2^23 bias of
+        // the byte -> float trick folded into the product: fma(2^23 + a, s, -2^23 s) = fl(a * s) exactly (2^23 s is
+        // exact), which is |fl((cq - cc) * s)| -- the reference's term up to the sign that the square removes. No
+        // query-side expansion, no separate subtraction: 9 instead of ~11.3 instructions per word and candidate.
+        constexpr bool ABSDIFF = QUANT == AB_QUANT_SQ8 && !IP;
+        if (ABSDIFF) {
+#pragma unroll
+          for (int p = 0; p < NP; p++) M[p] = p2mul(S[p], p2pack(-kMagic, -kMagic));  // -2^23 * s
+        } else {
+          word_pairs<QUANT>(q.x, Q);
+        }
         if (IP) {
 #pragma unroll
           for (int p = 0; p < NP; p++) Q[p] = p2fma(p2sub(Q[p], magic2), S[p], M[p]);  // min + cq * s
         }
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-          word_pairs<QUANT>(c == 0 ? c0.x : (c == 1 ? c1.x : c2.x), C);
+          const uint32_t cw = c == 0 ? c0.x : (c == 1 ? c1.x : c2.x);
+          word_pairs<QUANT>(ABSDIFF ? __vabsdiffu4(cw, q.x) : cw, C);
           unsigned long long acc = c == 0 ? a0 : (c == 1 ? a1 : a2);
 #pragma unroll
           for (int p = 0; p < NP; p++) {
             if (IP) {
               acc = p2fma(Q[p], p2fma(p2sub(C[p], magic2), S[p], M[p]), acc);  // (min + cq*s) * (min + cc*s)
+            } else if (ABSDIFF) {
+              const unsigned long long sd = p2fma(C[p], S[p], M[p]);  // |cq - cc| * s
+              acc = p2fma(sd, sd, acc);
             } else {
               const unsigned long long sd = p2mul(p2sub(Q[p], C[p]), S[p]);  // (cq - cc) * s
               acc = p2fma(sd, sd, acc);

@@ -74,6 +74,29 @@ def test_fails_loudly_without_a_gpu(cabi):
         calc_gt(x, x, 2)
 
 
+def test_multi_gpu_entry_points_validate_and_refuse_without_a_gpu(cabi):
+    """ab_group_* / ab_comm_* / ab_quant_minmax: bad arguments are rejected before any device work, and on a box
+    without a GPU the group refuses loudly instead of falling back to anything."""
+    lib = cabi.lib()
+    g = C.c_void_p()
+    p = cabi.Params(1, 0, 0, 1000, 32, -1)
+    devs = (C.c_int32 * 2)(0, 0)
+    assert lib.ab_group_create(None, devs, C.c_uint32(2), C.c_uint32(1), C.byref(g)) == -1
+    assert lib.ab_group_create(C.byref(p), devs, C.c_uint32(0), C.c_uint32(1), C.byref(g)) == -1      # no shards
+    assert lib.ab_group_create(C.byref(p), devs, C.c_uint32(17), C.c_uint32(1), C.byref(g)) == -1     # > 16 shards
+    assert lib.ab_group_fit(None, None, C.c_uint64(0), C.c_uint32(0), C.c_uint32(100)) == -1
+    assert lib.ab_group_batch_search(None, None, C.c_uint64(1), C.c_uint32(1), C.c_uint32(1), None, None) == -1
+    h = C.c_void_p()
+    buf = (C.c_uint8 * cabi.COMM_HANDLE_BYTES)()
+    assert lib.ab_comm_create(None, C.c_uint32(0), C.c_uint32(2), C.c_uint32(0), C.c_uint64(10), C.c_uint32(10), C.byref(h), buf) == -1
+    assert lib.ab_comm_connect(None, buf) == -1
+    assert lib.ab_quant_minmax(C.c_int32(0), None, C.c_uint64(0), C.c_uint32(0), None, None) in (-1, -2)
+    if _no_gpu(cabi):
+        assert lib.ab_group_create(C.byref(p), devs, C.c_uint32(2), C.c_uint32(1), C.byref(g)) == -2
+        assert b"no CPU fallback" in lib.ab_last_error()
+        assert lib.ab_index_build_graph_nsg(None, C.c_uint32(100), C.c_uint32(10)) < 0
+
+
 def test_bad_params_are_rejected_before_touching_the_device(cabi):
     lib = cabi.lib()
     h = C.c_void_p()
