@@ -81,6 +81,12 @@ __device__ __forceinline__ uint4 ldg128(const void *p) {
                : "l"(p));
   return r;
 }
+
+// Ask the TMA unit to pull `bytes` (a multiple of 16, 16-byte aligned) towards L2: one instruction per row, no
+// register or shared-memory landing zone, nothing to wait for.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 #endif
 
 }  // namespace ab

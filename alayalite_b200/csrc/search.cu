@@ -256,8 +256,31 @@ static SearchPlan plan_search_impl(int quant, int nchunks, int table_len, float 
     q.hash_dlimit = ((1u << std::min(16 - rbits, std::max(1, dbits_cap))) - 1) << rbits;
     return true;
   };
+  // Two-choice bucket format (visit_buckets): buckets of four 16-bit entries, an entry = which of the id's two
+  // buckets it sits in (1 bit) + the remainder of that scramble within the bucket (15 bits, 0xFFFF = empty). Needs
+  // at most 32767 ids of the id space per bucket; otherwise the slot format below, otherwise 32-bit ids.
+  static const int buckets_on = getenv("AB_HASH_BUCKETS") ? atoi(getenv("AB_HASH_BUCKETS")) : 1;
+  static const int buckets_minv = getenv("AB_HASH_BUCKETS_MINV") ? atoi(getenv("AB_HASH_BUCKETS_MINV")) : 0;
+  auto quotient_slots = quotient;
+  auto quotient_any = [&](uint32_t entries, SearchPlan &q) {
+    q.hash_buckets = 0;
+    if (buckets_on && ratio * static_cast<float>(ef) >= static_cast<float>(buckets_minv) && hash16 && entries >= 64 && entries < (1ull << idbits)) {
+      const uint32_t nb = entries / 4;
+      const uint64_t S = uint64_t(nb) << (32 - idbits);
+      const uint64_t M = (1ull << 32) / S + 1;
+      if (M <= 32767) {
+        q.hash_buckets = nb;
+        q.hash_rbits = 15;
+        q.hash_xshift = 32 - idbits;
+        q.hash_rmul = static_cast<uint32_t>(M);
+        q.hash_dlimit = 0;
+        return true;
+      }
+    }
+    return quotient_slots(entries, q);
+  };
   uint32_t entry_bytes = 4;
-  if (quotient(std::max(h, 2048u), p)) {  // 16-bit entries are cheap: never below 2048 of them (4 KB)
+  if (quotient_any(std::max(h, 2048u), p)) {  // 16-bit entries are cheap: never below 2048 of them (4 KB)
     h = std::max(h, 2048u);
     entry_bytes = 2;
   }
@@ -286,11 +309,11 @@ static SearchPlan plan_search_impl(int quant, int nchunks, int table_len, float 
     const uint32_t h12 = fit_entries(smem_limit, 12);
     if (h12 < h) h = std::max(512u, h12);
   }
-  entry_bytes = quotient(h, p) ? 2 : 4;
+  entry_bytes = quotient_any(h, p) ? 2 : 4;
   // the shard exchange merges in the warp's own shared memory: make sure the region is large enough
   if (other + size_t(h) * entry_bytes < min_warp_bytes) {
     h = static_cast<uint32_t>((min_warp_bytes - other + entry_bytes - 1) / entry_bytes + 63) & ~63u;
-    entry_bytes = quotient(h, p) ? 2 : 4;
+    entry_bytes = quotient_any(h, p) ? 2 : 4;
   }
   p.hash_size = h;
   p.hash_words = h * entry_bytes / 4;
@@ -344,10 +367,18 @@ void launch_search(int quant, const SearchPlan &plan, const SearchArgs &args_in,
   args.hash_words = plan.hash_words;
   static const int load_pct = getenv("AB_HASH_LOAD") ? std::min(95, std::max(10, atoi(getenv("AB_HASH_LOAD")))) : 75;
   args.hash_limit = static_cast<uint32_t>(uint64_t(plan.hash_size) * load_pct / 100);  // freeze the table at this load
+  args.hash_buckets = plan.hash_buckets;
+  if (plan.hash_buckets) args.hash_limit = 0xFFFFFFFFu;  // the bucket format needs no freeze: an id whose two buckets are full moves on
   args.hash_rbits = plan.hash_rbits;
   args.hash_xshift = plan.hash_xshift;
   args.hash_rmul = plan.hash_rmul;
   args.hash_dlimit = plan.hash_dlimit;
+  // Long code rows (TPV >= 16: six rows per pass, a hop of ~23 new neighbours is four passes): the rows of the later
+  // passes are requested from the TMA unit when the first pass starts (SQ8 d = 960, ef 180: 12.1 -> 11.6 ms). Measured
+  // and left off elsewhere: SQ4 d = 768 (-1 %), raw d = 128 (+-1 %); the speculative variant (bit 1: every neighbour
+  // before the visited filter) costs 1-10 % everywhere.
+  const int prefetch = getenv("AB_PREFETCH") ? atoi(getenv("AB_PREFETCH")) : ((quant != AB_QUANT_NONE && plan.tpv >= 16) ? 1 : 0);
+  args.prefetch = prefetch;
   const bool ip = args.metric != AB_METRIC_L2;
   if (quant == AB_QUANT_NONE) {
     ip ? launch_search_raw<true>(plan, args, stream) : launch_search_raw<false>(plan, args, stream);

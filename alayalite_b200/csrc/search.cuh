@@ -58,6 +58,7 @@ struct SearchArgs {
   int hash_xshift;              // 32 - bits of the id space
   uint32_t hash_rmul;           // remainder = umulhi(low word of scramble * entries, hash_rmul)
   uint32_t hash_dlimit;         // first invalid entry code (displacement range exhausted)
+  uint32_t hash_buckets;        // > 0: two-choice table of this many buckets of four 16-bit entries (see visit_buckets)
   // Visited ids that do not fit the shared-memory table continue in the warp's private overflow table in global
   // memory: [slots, ovf_size + kSpillList] words per slot -- an open-addressing table of ids (all 0xFFFFFFFF between
   // queries) followed by a scratch list of the entries a query claimed, so that giving the table back clean costs
@@ -70,6 +71,10 @@ struct SearchArgs {
   uint32_t *big_flags;          // [n_big] 0 = free, 1 = claimed
   uint32_t n_big;
   size_t big_words;
+  // bit 0: rows of the later passes of a hop are requested from the TMA unit (bulk L2 prefetch) while the first pass
+  // is evaluated; bit 1: the rows of every neighbour of the node being expanded are requested before the visited
+  // filter runs (speculative: rows of already visited neighbours are fetched too)
+  int prefetch;
   unsigned long long *stats;    // {ndc level 0, hops, ndc overlay, queries that used the overflow table,
                                 //  queries that went on to a pooled bitmap, ids put into overflow tables}
 };
@@ -101,6 +106,7 @@ struct SearchPlan {
   uint32_t hash_words;  // 32-bit words of shared memory the table takes
   int hash_rbits, hash_xshift;
   uint32_t hash_rmul, hash_dlimit;
+  uint32_t hash_buckets;  // > 0: two-choice bucket format
   size_t smem_bytes;
   int slots;          // ctas * warps_per_cta (overflow-table slots needed)
   int max_slots;      // slots any plan for this batch size could need (workspace sizing)

@@ -144,6 +144,65 @@ __device__ __noinline__ void visit_overflow_release(uint32_t *tab, uint32_t ovf_
   __syncwarp();
 }
 
+// bits 15 / 31 are CLEAR where the low / high halfword of p ^ r is zero (exact per halfword: no carry crosses the halves)
+__device__ __forceinline__ uint32_t differs_halves(uint32_t p, uint32_t r) {
+  const uint32_t t = p ^ r;
+  return ((t & 0x7FFF7FFFu) + 0x7FFF7FFFu) | t;
+}
+
+// Level 1 of the visited set, two-choice bucket format (a.hash_buckets > 0). The table is hash_buckets buckets of four
+// 16-bit entries, one 64-bit shared load each, filled from entry 0 upwards (0xFFFF = free). An id has two candidate
+// buckets, taken from two different bijective scrambles of the b-bit id space (odd multipliers mod 2^b); an entry
+// stores which of the two placed it (bit 15) and the remainder of THAT scramble inside its bucket (15 bits; at most
+// 32767 ids of the id space per bucket, the plan checks), so an entry equal to (which, remainder) inside bucket B can
+// only belong to one id: exact, like the slot format. A lookup reads both buckets and is a hit or a miss at once --
+// no probe sequence, so the warp does not iterate as long as its unluckiest lane (the slot format at 3/4 load: a
+// third of the kernel time at ef 280). A new id goes to the bucket with more free entries (ties: the first); with
+// four entries per bucket that places 99.5 % of the ids at 75 % load and 96 % at 90 %. An id that finds both buckets
+// full continues in the warp's overflow table (levels 2 / 3) -- and so will every later lookup of it, because
+// buckets never lose entries during a query. The loop below only repeats for lanes whose CAS lost against another
+// lane of the same warp (same bucket, same free entry).
+__device__ __forceinline__ bool visit_buckets(const SearchArgs &a, Visited &vs, uint32_t key, bool active, bool &to_l2) {
+  const uint32_t nb = a.hash_buckets;
+  const uint32_t x1 = (key * 0x9E3779B1u) << a.hash_xshift, x2 = (key * 0x85EBCA6Bu) << a.hash_xshift;
+  const uint32_t b1 = __umulhi(x1, nb), b2 = __umulhi(x2, nb);
+  const uint32_t c1 = __umulhi(x1 * nb, a.hash_rmul), c2 = __umulhi(x2 * nb, a.hash_rmul) | 0x8000u;
+  const uint32_t r1 = c1 * 0x10001u, r2 = c2 * 0x10001u;
+  const volatile unsigned long long *tab = reinterpret_cast<const volatile unsigned long long *>(vs.hash);
+  bool is_new = false, pending = active;
+  to_l2 = false;
+  while (__any_sync(kFull, pending)) {
+    if (pending) {
+      const unsigned long long B1 = tab[b1], B2 = tab[b2];
+      const uint32_t p0 = static_cast<uint32_t>(B1), p1 = static_cast<uint32_t>(B1 >> 32);
+      const uint32_t q0 = static_cast<uint32_t>(B2), q1 = static_cast<uint32_t>(B2 >> 32);
+      const uint32_t all_differ = differs_halves(p0, r1) & differs_halves(p1, r1) & differs_halves(q0, r2) & differs_halves(q1, r2);
+      if ((all_differ & 0x80008000u) != 0x80008000u) {
+        pending = false;  // seen before
+      } else {
+        // free entries are a suffix of the bucket: 16 leading one-bits per free entry
+        const int f1 = p1 == kFull ? 2 + (__clz(~p0) >> 4) : (__clz(~p1) >> 4);
+        const int f2 = q1 == kFull ? 2 + (__clz(~q0) >> 4) : (__clz(~q1) >> 4);
+        if ((f1 | f2) == 0) {
+          pending = false;
+          to_l2 = true;
+        } else {
+          const bool first = f1 >= f2;
+          const int used = 4 - (first ? f1 : f2);  // the entry to claim
+          const int wi = used >> 1, sh = (used & 1) << 4;
+          const uint32_t old = first ? (wi ? p1 : p0) : (wi ? q1 : q0);
+          const uint32_t want = old ^ ((0xFFFFu ^ (first ? c1 : c2)) << sh);
+          if (atomicCAS(&vs.hash[(first ? b1 : b2) * 2u + wi], old, want) == old) {
+            is_new = true;
+            pending = false;
+          }
+        }
+      }
+    }
+  }
+  return is_new;
+}
+
 // Warp-collective: every lane with `active` tests-and-sets its key; true if the key was not yet in the set.
 // The probe loop is driven by a warp vote, so the warp stays converged (a per-lane probe loop leaves the
 // lanes split under independent thread scheduling, and every later warp-level primitive then takes the
@@ -164,7 +223,9 @@ __device__ __forceinline__ bool visit(const SearchArgs &a, Visited &vs, uint32_t
   bool is_new = false;
   bool pending = active;
   bool to_bitmap = false;
-  if (a.hash_rbits != 0) {
+  if (a.hash_buckets != 0) {
+    is_new = visit_buckets(a, vs, key, active, to_bitmap);
+  } else if (a.hash_rbits != 0) {
     const uint32_t x = (key * 0x9E3779B1u) << a.hash_xshift;
     uint32_t slot = __umulhi(x, hsize);
     uint32_t code = __umulhi(x * hsize, a.hash_rmul);  // displacement 0
@@ -492,6 +553,11 @@ __device__ __forceinline__ float eval_lanes_multi(const SearchArgs &a, const War
   __syncwarp();
   const int g = lane / TPV, lg = lane % TPV;
   const uint8_t *lane_base = a.rows + lg * 16;
+  if ((a.prefetch & 1) && cnt > INFL * G) {
+    // more than one pass: the rows of the later passes start their way to L2 now, one bulk request per row
+    const int k = INFL * G + lane;
+    if (k < cnt) bulk_prefetch_l2(a.rows + size_t(ws.cand[k]) * a.row_stride, static_cast<uint32_t>(a.nchunks) * 16u);
+  }
   for (int base = 0; base < cnt; base += INFL * G) {
     const int rem = cnt - base;  // warp-uniform
     const int k0 = base + g, k1 = k0 + G, k2 = k1 + G;
@@ -753,6 +819,7 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
       hops++;
       const uint32_t empties = __ballot_sync(kFull, v == kEmptyId);
       const int cnt = empties ? __ffs(empties) - 1 : kR;
+      if ((a.prefetch & 2) && lane < cnt) bulk_prefetch_l2(a.rows + size_t(v) * a.row_stride, static_cast<uint32_t>(a.nchunks) * 16u);
       if (!vs.spilled && nvis + kR > a.hash_limit) vs.spilled = true;
       const bool is_new = visit(a, vs, v, lane < cnt);
       const uint32_t newmask = __ballot_sync(kFull, is_new);

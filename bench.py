@@ -236,12 +236,13 @@ def row_bytes_of(cfg):
     return (b + 63) // 64 * 64  # whole 64-byte-strided rows are fetched
 
 
-def algorithmic_bytes(cfg, stats):
+def algorithmic_bytes(cfg, stats, nq):
     """(ndc_L0 + ndc_overlay) * row_bytes + hops * R * 4, plus the raw rows of the re-rank for SQ spaces
     (topk ids + id 0: what the reference's re-rank over a zero-filled res_pool really touches)."""
     b = (stats["ndc"] + stats["overlay"]) * row_bytes_of(cfg) + stats["hops"] * 128
     if cfg["quant"] != "none":
-        b += stats["queries"] * (cfg["topk"] + 1) * ((cfg["dim"] * 4 + 63) // 64 * 64)
+        # (nq of THIS launch: the device-resident entry point does not report a query count in its statistics)
+        b += nq * (cfg["topk"] + 1) * ((cfg["dim"] * 4 + 63) // 64 * 64)
     return b
 
 
@@ -336,7 +337,7 @@ def run_block(name, cfg, args, torch, dev, local_rank, stream, peaks, cpu=True, 
     e2e_pinned = nq * args.steps / (time.perf_counter() - t0)
 
     hbm, _, peak_src = peaks
-    alg = algorithmic_bytes(cfg, stats)
+    alg = algorithmic_bytes(cfg, stats, nq)
     achieved = alg / (ms * 1e-3) / 1e9
     out = {
         "workload": cfg["workload"], "ef": ef, "recall": rec, "recall_k": k, "target_met": met, "recall_by_ef": hist[-6:],

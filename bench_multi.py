@@ -175,7 +175,7 @@ def run_grid(cfg, S, R, args, torch, dist, dev, local_rank, stream, rank, world,
     total_ms, alone_ms, e2e_s = float(red[0]), float(red[1]), float(red[2])
     hbm, _, peak_src = load_peaks()
     k_ms = float(np.mean(alone))
-    alg = algorithmic_bytes(cfg, stats)
+    alg = algorithmic_bytes(cfg, stats, nq)
     ach = alg / (k_ms * 1e-3) / 1e9
     step_ms = total_ms / args.steps
     out = {

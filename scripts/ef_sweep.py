@@ -11,6 +11,7 @@ ap.add_argument("--quant", default="none"); ap.add_argument("--metric", default=
 ap.add_argument("--latent", type=int, default=16); ap.add_argument("--topk", type=int, default=10)
 ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--device-gen", action="store_true", help="generate rows on the GPU (bench.py's generator)")
+ap.add_argument("--prefetch", default="", help="comma-separated AB_PREFETCH values to run every ef with")
 ap.add_argument("efs", nargs="*", type=int)
 a = ap.parse_args()
 efs = a.efs or [20, 52, 100]
@@ -32,8 +33,10 @@ stream = torch.cuda.Stream()
 d_q = torch.from_numpy(q).cuda(); d_ids = torch.zeros((nq, k), dtype=torch.int32, device="cuda"); d_dist = torch.zeros((nq, k), device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 with torch.cuda.stream(stream):
-    for ef in efs:
+    for ef, pf in [(e, p) for e in efs for p in (a.prefetch.split(",") if a.prefetch else [None])]:
         if ef < k: continue
+        if pf is not None:
+            os.environ["AB_PREFETCH"] = pf; print(f"AB_PREFETCH={pf}", end=" ")
         ts = []
         for it in range(8):
             flush.zero_()

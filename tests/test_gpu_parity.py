@@ -351,7 +351,7 @@ def test_pinned_host_buffers_are_used_in_place(cabi, small_sets, quant):
 
 
 def test_visited_table_formats_agree(cabi, tmp_path):
-    """16-bit quotient entries, 32-bit id entries, a table far too small (everything continues in the bitmap) and a
+    """Two-choice buckets of 16-bit entries (the default), 16-bit slot entries, 32-bit id entries, a table far too small (everything continues in the bitmap) and a
     table whose displacement range overflows must all give the same traversal, bit for bit."""
     import subprocess
     import sys
@@ -367,19 +367,21 @@ def test_visited_table_formats_agree(cabi, tmp_path):
     np.save(folder / "n.npy", np.array(n))
     probe = os.path.join(os.path.dirname(__file__), "_visited_probe.py")
     runs = {}
-    for name, env in {"default": {}, "ids32": {"AB_HASH16": "0"}, "tiny16": {"AB_HASH_FACTOR": "0.05"},
+    for name, env in {"default": {}, "ids32": {"AB_HASH16": "0"}, "tiny16": {"AB_HASH_FACTOR": "0.05", "AB_HASH_BUCKETS": "0"},
                       "tiny32": {"AB_HASH16": "0", "AB_HASH_FACTOR": "0.05"},
-                      "nodisp": {"AB_HASH_DBITS_CAP": "1"}}.items():  # home slot only: most probes end in the bitmap
+                      "slots16": {"AB_HASH_BUCKETS": "0"},  # one-entry slots with double hashing instead of two-choice buckets
+                      "tinyb": {"AB_HASH_FACTOR": "0.05"},  # buckets, table far too small: both buckets of most ids are full
+                      "nodisp": {"AB_HASH_DBITS_CAP": "1", "AB_HASH_BUCKETS": "0"}}.items():  # home slot only: most probes end in the bitmap
         out = str(tmp_path / f"{name}.npz")
         r = subprocess.run([sys.executable, probe, str(folder), out, "16", "64", "300"], env={**os.environ, **env},
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         runs[name] = np.load(out)
     for ef in (16, 64, 300):
-        for name in ("ids32", "tiny16", "tiny32", "nodisp"):
+        for name in ("ids32", "tiny16", "tiny32", "slots16", "tinyb", "nodisp"):
             assert np.array_equal(runs[name][f"ids{ef}"], runs["default"][f"ids{ef}"]), (name, ef)
             assert np.array_equal(runs[name][f"dist{ef}"], runs["default"][f"dist{ef}"]), (name, ef)
-    assert int(runs["tiny16"]["bitmap300"]) > 0 and int(runs["tiny32"]["bitmap300"]) > 0
+    assert int(runs["tiny16"]["bitmap300"]) > 0 and int(runs["tiny32"]["bitmap300"]) > 0 and int(runs["tinyb"]["bitmap300"]) > 0
     assert int(runs["nodisp"]["bitmap64"]) > 0
     assert int(runs["default"]["bitmap64"]) == 0
 
