@@ -651,7 +651,8 @@ int ab_debug_search_plan(int32_t quant, uint32_t row_chunks, uint32_t ef, uint64
     AB_CHECK(out != nullptr && row_chunks >= 1 && ef >= 1 && sm_count >= 1 && smem_limit >= 48 * 1024, AB_ERR_INVALID,
              "bad plan query");
     const int table_len = quant == AB_QUANT_SQ8 ? row_chunks * 16 : (quant == AB_QUANT_SQ4 ? row_chunks * 32 : 0);
-    const SearchPlan p = plan_search(quant, static_cast<int>(row_chunks), table_len, 0.f, ef, static_cast<uint32_t>(nq),
+    const float vr = getenv("AB_DEBUG_VISIT_RATIO") ? static_cast<float>(atof(getenv("AB_DEBUG_VISIT_RATIO"))) : 0.f;  // developer knob
+    const SearchPlan p = plan_search(quant, static_cast<int>(row_chunks), table_len, vr, ef, static_cast<uint32_t>(nq),
                                      static_cast<uint32_t>(n_rows), sm_count, smem_limit);
     out[0] = p.warps_per_cta;
     out[1] = p.ctas_per_sm;

@@ -19,5 +19,6 @@ for ef in efs:
     ids, dist = ix.batch_search_with_distance(q, 10, ef)
     res[f"ids{ef}"] = ids
     res[f"dist{ef}"] = dist
-    res[f"bitmap{ef}"] = np.array(ix.stats()["spilled"])
+    res[f"bitmap{ef}"] = np.array(ix.stats()["spilled"])  # queries that used their overflow table (level 2)
+    res[f"big{ef}"] = np.array(ix.stats()["bitmap"])  # queries that went on to a pooled bitmap (level 3)
 np.savez(out, **res)

@@ -371,6 +371,8 @@ def test_visited_table_formats_agree(cabi, tmp_path):
                       "tiny32": {"AB_HASH16": "0", "AB_HASH_FACTOR": "0.05"},
                       "slots16": {"AB_HASH_BUCKETS": "0"},  # one-entry slots with double hashing instead of two-choice buckets
                       "tinyb": {"AB_HASH_FACTOR": "0.05"},  # buckets, table far too small: both buckets of most ids are full
+                      # tiny level 1, 256-entry level 2, two pooled bitmaps for all warps: most ids end in level 3 and warps queue for a bitmap
+                      "level3": {"AB_HASH_FACTOR": "0.05", "AB_OVF_SIZE": "256", "AB_BIG_SLOTS": "2"},
                       "nodisp": {"AB_HASH_DBITS_CAP": "1", "AB_HASH_BUCKETS": "0"}}.items():  # home slot only: most probes end in the bitmap
         out = str(tmp_path / f"{name}.npz")
         r = subprocess.run([sys.executable, probe, str(folder), out, "16", "64", "300"], env={**os.environ, **env},
@@ -378,10 +380,11 @@ def test_visited_table_formats_agree(cabi, tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         runs[name] = np.load(out)
     for ef in (16, 64, 300):
-        for name in ("ids32", "tiny16", "tiny32", "slots16", "tinyb", "nodisp"):
+        for name in ("ids32", "tiny16", "tiny32", "slots16", "tinyb", "level3", "nodisp"):
             assert np.array_equal(runs[name][f"ids{ef}"], runs["default"][f"ids{ef}"]), (name, ef)
             assert np.array_equal(runs[name][f"dist{ef}"], runs["default"][f"dist{ef}"]), (name, ef)
     assert int(runs["tiny16"]["bitmap300"]) > 0 and int(runs["tiny32"]["bitmap300"]) > 0 and int(runs["tinyb"]["bitmap300"]) > 0
+    assert int(runs["level3"]["big300"]) > 0 and int(runs["default"]["big300"]) == 0
     assert int(runs["nodisp"]["bitmap64"]) > 0
     assert int(runs["default"]["bitmap64"]) == 0
 
