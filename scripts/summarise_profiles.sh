@@ -7,7 +7,10 @@ for pair in "prof_r02_raw10m|beam_search_kernel, raw rows, 10M x 128 fp32 L2, 10
             "prof_r02_ef280_final|beam_search_kernel, the same launch AFTER the round-2 changes (double hashing, destination-tile merge, six rows in flight)" \
             "prof_r02_c5_ef144|beam_search_kernel, one C5 shard: 12.5M x 96 fp32 L2, ef 144" \
             "prof_r02_sq8_c3|beam_search_kernel, SQ8 codes, C3 1M x 960 L2, ef 180" \
-            "prof_r02_sq4_c4|beam_search_kernel, SQ4 codes, C4 shape 2M x 768 inner product, top-100, ef 160"; do
+            "prof_r02_sq4_c4|beam_search_kernel, SQ4 codes, C4 shape 2M x 768 inner product, top-100, ef 160" \
+            "prof_r02b_ef280|beam_search_kernel, hard variant at ef 280 with the two-choice bucket table (final code of round 2)" \
+            "prof_r02b_sq8_c3|beam_search_kernel, SQ8 C3 1M x 960 ef 180, final code (bucket table, VABSDIFF4 decode, bulk L2 prefetch of later passes)" \
+            "prof_r02b_sq4_c4|beam_search_kernel, SQ4 2M x 768 inner product top-100 ef 160, final code (bucket table)"; do
   f=${pair%%|*}; title=${pair#*|}
   [ -f gpurun_out/$f.ncu-rep ] || continue
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > /tmp/_raw.csv 2>/dev/null
