@@ -117,20 +117,22 @@ def test_search_bit_exact_on_integer_grid(cabi, orc, small_sets, metric):
     reference's ids bit for bit, ties included, and even the counters (distance calls, hops)."""
     base, q = small_sets["grid"]
     o, ix = _pair(cabi, orc, base, metric, "none")
-    for ef, k in ((10, 10), (32, 10), (50, 5), (100, 32), (300, 100)):
+    # (ef 33 .. 64 and 65 .. 96: the two- and three-entries-per-lane merges; above: the tile merge)
+    for ef, k in ((10, 10), (32, 10), (50, 5), (64, 10), (65, 10), (68, 10), (80, 20), (96, 10), (97, 10), (100, 32), (300, 100)):
         want = o.batch_search(q, k, ef)
         got = ix.batch_search(q, k, ef)
         assert np.array_equal(got, want), (metric, ef, k)
-    ids, dist, sizes = ix.traverse(q[:40], 64)
-    st = ix.stats()
-    ndc = hops = ov = 0
-    for i in range(40):
-        pi, pd, s = o.traverse(q[i], 64)
-        assert sizes[i] == len(pi)
-        assert np.array_equal(ids[i, : sizes[i]], pi)
-        assert np.array_equal(dist[i, : sizes[i]], pd)
-        ndc, hops, ov = ndc + s["ndc"], hops + s["hops"], ov + s["overlay"]
-    assert (st["ndc"], st["hops"], st["overlay"]) == (ndc, hops, ov)
+    for ef_t in (64, 90):
+        ids, dist, sizes = ix.traverse(q[:40], ef_t)
+        st = ix.stats()
+        ndc = hops = ov = 0
+        for i in range(40):
+            pi, pd, s = o.traverse(q[i], ef_t)
+            assert sizes[i] == len(pi)
+            assert np.array_equal(ids[i, : sizes[i]], pi)
+            assert np.array_equal(dist[i, : sizes[i]], pd)
+            ndc, hops, ov = ndc + s["ndc"], hops + s["hops"], ov + s["overlay"]
+        assert (st["ndc"], st["hops"], st["overlay"]) == (ndc, hops, ov)
 
 
 @pytest.mark.parametrize("seed", range(10))
