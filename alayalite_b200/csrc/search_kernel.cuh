@@ -4,9 +4,10 @@
 // Design. One warp owns one query at a time and pulls the next query index from a global counter (the role of the
 // reference's task queue). Per hop the warp
 //   1. holds the 128-byte adjacency row of the node being expanded (one coalesced load, lane j <- neighbour j),
-//   2. filters the neighbours through the visited set: an exact open-addressing table in shared memory (16-bit
-//      quotient entries or 32-bit ids, vote-driven probe loop); a query that outgrows it continues in the warp's
-//      private overflow table in global memory (sized from ef, not from the number of rows) and, past that, in a
+//   2. filters the neighbours through the visited set: an exact table in shared memory (16-bit quotient entries in
+//      two-choice buckets of four -- one 64-bit load per bucket, no probe sequence --, or one-entry slots with a
+//      vote-driven probe loop, or 32-bit ids, whichever the id range allows); a query that outgrows it continues in the
+//      warp's private overflow table in global memory (sized from ef, not from the number of rows) and, past that, in a
 //      pooled N-bit bitmap (the reference's structure) -- never a false "visited" or "new",
 //   3. evaluates all unvisited neighbours: sub-warps of TPV lanes per candidate row, 128-bit loads, three candidates
 //      per sub-warp in flight, query chunks read from shared memory after the loads are issued, packed f32x2 math,
