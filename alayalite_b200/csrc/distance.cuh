@@ -417,7 +417,9 @@ __device__ __forceinline__ void word_pairs(uint32_t w, unsigned long long (&out)
     out[0] = p2pack(byte_as_magic(w, 0), byte_as_magic(w, 1));
     out[1] = p2pack(byte_as_magic(w, 2), byte_as_magic(w, 3));
   } else {
-    const uint32_t lo = w & 0x0F0F0F0Fu, hi = (w >> 4) & 0x0F0F0F0Fu;
+    // the high nibbles stay where they are (16 x code): the staged scale table holds s / 16 for the odd entries, so
+    // (16 c) * (s / 16) is the same real product as c * s and every term rounds exactly as before, one shift less
+    const uint32_t lo = w & 0x0F0F0F0Fu, hi = w & 0xF0F0F0F0u;
 #pragma unroll
     for (int k = 0; k < 4; k++) out[k] = p2pack(byte_as_magic(lo, k), byte_as_magic(hi, k));
   }

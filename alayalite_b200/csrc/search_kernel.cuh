@@ -655,7 +655,8 @@ __global__ void __launch_bounds__((INFL == 6 && CPL == 4) ? 192 : 256,
         at = ((e >> 2) * a.nchunks + chunk) * 4 + (e & 3);
       }
       if (CPL == 0 || i / DPC < a.nchunks) {
-        s_scale[at] = a.scale[i];
+        // packed SQ4 path: high nibbles are decoded as 16 x code (distance.cuh word_pairs), their scale is s / 16
+        s_scale[at] = (QUANT == AB_QUANT_SQ4 && CPL > 0 && (i & 1)) ? a.scale[i] * 0.0625f : a.scale[i];
         s_vmin[at] = a.vmin[i];
       }
     }
