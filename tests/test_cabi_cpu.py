@@ -150,3 +150,25 @@ def test_search_plan_policy(cabi):
         assert p["warps_per_cta"] * p["ctas_per_sm"] >= floor and p["smem_per_cta"] + kb <= 227 * kb, (ef, p)
     with pytest.raises(Exception):
         cabi.debug_search_plan("none", 0, 52, 10, 10)
+
+
+@pytest.mark.parametrize("idbits,entries", [(15, 2048), (20, 2112), (20, 6720), (22, 2560)])
+def test_bucket_entries_identify_ids(idbits, entries):
+    """The exactness argument of the two-choice bucket table (search_kernel.cuh visit_buckets), replayed on the host
+    with the kernel's 32-bit arithmetic: for either scramble, (bucket, remainder) is injective over the whole id
+    space, remainders stay below 2^15 - 1 (so no entry equals the empty mark 0xFFFF), and the plan's condition
+    M <= 32767 is what guarantees it."""
+    nb = entries // 4
+    S = nb << (32 - idbits)
+    M = (1 << 32) // S + 1          # search.cu plan_search_impl: remainder multiplier of the bucket format
+    assert M <= 32767
+    ids = np.arange(1 << idbits, dtype=np.uint64)
+    for mult, which in ((0x9E3779B1, 0), (0x85EBCA6B, 0x8000)):
+        x = ((ids * mult) & 0xFFFFFFFF) << (32 - idbits) & 0xFFFFFFFF          # (key * C) << xshift, 32-bit
+        bucket = (x * nb) >> 32                                                # __umulhi(x, nb)
+        rem = (((x * nb) & 0xFFFFFFFF) * M) >> 32                              # __umulhi(x * nb, M)
+        assert bucket.max() < nb and rem.max() < M
+        entry = rem | which
+        assert (entry != 0xFFFF).all()
+        code = bucket * 65536 + entry
+        assert np.unique(code).size == ids.size, (idbits, entries, hex(mult))
